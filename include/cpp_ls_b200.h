@@ -1,0 +1,129 @@
+/*
+ * cpp_ls_b200.h -- C ABI of the B200 (sm_100a) least-squares / ALS / similarity library.
+ *
+ * The shared object built from movie_recommender_b200/csrc is a DROP-IN for the reference's
+ * `cpp_ls_lib.so`: section 1 declares exactly the five `extern "C"` symbols the reference's
+ * ctypes wrapper binds (reference: cpp/ls_lib/ls_linux_dll.cpp:8-103, loaded by
+ * python/full_data/cpp_ls.py:5-14), with identical argument lists, in/out conventions and
+ * return values.  Section 2 onwards are extensions the reference does not have (device-resident
+ * handles so that a benchmark can time sweeps with inputs already in HBM, the GPU-native solver
+ * modes, the index build and similarity kernels exposed for parity tests).
+ *
+ * Plain pointers and sizes only; every pointer is a HOST pointer unless its name starts with
+ * `d_`.  The caller owns every buffer (ls_linux_dll.cpp:42-46, 95-99: delete_values = false).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * MRB_ERR_CUDA.
+ *
+ * Error convention.  The reference has none (return value = iteration count; a dimension
+ * mismatch throws a string literal across `extern "C"`, matrix.cpp:403-405, i.e. terminates the
+ * process).  Here: return value >= 0 is the reference's iteration count; a negative value is an
+ * error code and mrb_last_error() describes it.  Never negative on a success path.
+ */
+#ifndef CPP_LS_B200_H
+#define CPP_LS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MRB_API __attribute__((visibility("default")))
+#else
+#define MRB_API
+#endif
+
+#define MRB_ERR_CUDA (-1)      /* CUDA runtime failure: no device, out of memory, launch error */
+#define MRB_ERR_ARGUMENT (-2)  /* dimension mismatch / id out of range / unsupported size      */
+#define MRB_ERR_INTERNAL (-3)
+
+/* ------------------------------------------------------------------------------------------
+ * 1. Drop-in symbols (same names, same signatures as the reference).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Replaces ls_linux_dll.cpp:8-16.  In the reference `thread_count` is the number of std::threads
+ * and thereby fixes every floating-point summation order (matrix.cpp:7-16, 375-396, 418-449).
+ * Here it is the reference thread count whose summation order the bit-faithful algorithms
+ * (algorithm 1 and 2) reproduce: results are bit-identical to the reference run with the same
+ * thread_count.  Values < 1 are treated as 1.  Default 4 (ls_linux_dll.cpp:6).  Round-trips
+ * through get_thread_count() (the health check of python/full_data/cpp_ls.py:23-36). */
+MRB_API void set_thread_count(int thread_count);
+MRB_API int get_thread_count(void);
+
+/* Replaces ls_linux_dll.cpp:28-50 -> cg_least_squares (matrix.cpp:456-529).
+ * CSR A (A_row_indices[A_rows+1], A_col_indices[nnz], A_values[nnz]); x_values is x0 on entry
+ * and the solution on exit; *final_rr receives the last r.r.  Returns the iteration count. */
+MRB_API int cg_least_squares_from_python(int A_rows, int A_cols, int* A_row_indices, int* A_col_indices,
+                                 double* A_values, int b_length, double* b_values, int x_length,
+                                 double* x_values, double min_r_decrease, int max_iteration,
+                                 double* final_rr);
+
+/* Replaces ls_linux_dll.cpp:54-77 -> cg_least_squares2 (matrix.cpp:536-613): the same CG with
+ * A^T products taken through the explicit (stable) transpose. */
+MRB_API int cg_least_squares2_from_python(int A_rows, int A_cols, int* A_row_indices, int* A_col_indices,
+                                  double* A_values, int b_length, double* b_values, int x_length,
+                                  double* x_values, double min_r_decrease, int max_iteration,
+                                  double* final_rr);
+
+/* Replaces ls_linux_dll.cpp:81-103 -> als (matrix.cpp:744-893).
+ * COO ratings in any order; user_factors (num_users*(k+1)) and item_factors (num_items*k) are
+ * initial values on entry and results on exit.  Returns the sweep counter at exit.
+ *   algorithm 1, 2 : the reference's two variants, bit-faithful at get_thread_count().
+ *   algorithm 3    : (extension) the same CG with global alpha/beta and the same stopping rule,
+ *                    run on per-row Gram blocks with GPU-native summation order.
+ *   algorithm 4    : (extension) every half-sweep solves each row's normal equations exactly
+ *                    (gathered Gram matrix + in-shared-memory Cholesky).
+ * Any other value behaves like 2, as in the reference (matrix.cpp:817-828). */
+MRB_API int als_from_python(int* user_ids, int* item_ids, int ratings_length, double* ratings_values,
+                    int num_item_factors, int user_factors_length, double* user_factors_values,
+                    int item_factors_length, double* item_factors_values, double min_r_decrease,
+                    int max_iteration, int algorithm);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Extensions: diagnostics.
+ * ---------------------------------------------------------------------------------------- */
+MRB_API const char* mrb_last_error(void);   /* message of the last failing call on this thread */
+MRB_API int mrb_device_count(void);         /* number of visible CUDA devices (0 if none / no driver) */
+MRB_API const char* mrb_build_info(void);   /* "sm_100a ..." */
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Extensions: index build (K4), exposed for bit-exact parity tests.
+ *    Replaces sparse_matrix_transpose and helpers (matrix.cpp:617-738, 251-297).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Stable grouping of positions 0..n-1 by keys[] in [0, num_groups): ptr_out[num_groups+1],
+ * idx_out[n]; identical to numpy.argsort(keys, kind="stable") + bincount/cumsum. */
+MRB_API int mrb_group_by(const int* keys, int n, int num_groups, int* ptr_out, int* idx_out);
+
+/* Stable CSR -> CSC: t_ptr[cols+1], t_row[nnz], t_val[nnz]. */
+MRB_API int mrb_csr_transpose(int rows, int cols, const int* rowptr, const int* colidx, const double* vals,
+                      int* t_ptr, int* t_row, double* t_val);
+
+/* ------------------------------------------------------------------------------------------
+ * 4. Extensions: device-resident ALS problem (inputs stay in HBM between calls).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mrb_als_problem mrb_als_problem;
+
+typedef struct mrb_als_run_info {
+    int sweeps_returned;   /* what als_from_python returns */
+    int sweeps_run;        /* (user, item) half-sweep pairs executed */
+    int cg_iterations;     /* total inner CG iterations (CG algorithms) */
+    double last_rr;        /* item-solve normal-equation residual of the last sweep */
+    float device_ms;       /* CUDA-event time of the sweep loop on the problem's stream */
+    float index_build_ms;  /* CUDA-event time of the two stable groupings at creation */
+} mrb_als_run_info;
+
+MRB_API int mrb_als_create(const int* user_ids, const int* item_ids, int num_ratings,
+                   const double* ratings, int num_item_factors, int num_users, int num_items,
+                   mrb_als_problem** out);
+MRB_API int mrb_als_set_factors(mrb_als_problem* p, const double* user_factors, const double* item_factors);
+MRB_API int mrb_als_get_factors(mrb_als_problem* p, double* user_factors, double* item_factors);
+/* Copies out the two groupings (u_ptr[num_users+1], u_idx[nnz], i_ptr[num_items+1], i_idx[nnz]). */
+MRB_API int mrb_als_get_index(mrb_als_problem* p, int* u_ptr, int* u_idx, int* i_ptr, int* i_idx);
+MRB_API int mrb_als_run(mrb_als_problem* p, int algorithm, double min_r_decrease, int max_iteration,
+                mrb_als_run_info* info);
+MRB_API void mrb_als_destroy(mrb_als_problem* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPP_LS_B200_H */

@@ -1,0 +1,95 @@
+"""ctypes loader for the CUDA library (movie_recommender_b200/cpp_ls_lib.so).
+
+The shared object is built in-tree by ``make -C movie_recommender_b200/csrc`` (or
+``__graft_entry__.build()``).  It is the product: if it is missing the import fails loudly --
+there is no fallback implementation.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "cpp_ls_lib.so")
+
+_I = ctypes.POINTER(ctypes.c_int)
+_D = ctypes.POINTER(ctypes.c_double)
+
+ERR_CUDA, ERR_ARGUMENT, ERR_INTERNAL = -1, -2, -3
+
+
+class AlsRunInfo(ctypes.Structure):
+    """mrb_als_run_info (include/cpp_ls_b200.h)."""
+    _fields_ = [("sweeps_returned", ctypes.c_int), ("sweeps_run", ctypes.c_int),
+                ("cg_iterations", ctypes.c_int), ("last_rr", ctypes.c_double),
+                ("device_ms", ctypes.c_float), ("index_build_ms", ctypes.c_float)]
+
+
+class CppLsError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("cpp_ls_lib error %d: %s" % (code, message))
+        self.code = code
+
+
+def _declare(dll):
+    c_int, c_double, c_void_p = ctypes.c_int, ctypes.c_double, ctypes.c_void_p
+    dll.set_thread_count.restype = None
+    dll.set_thread_count.argtypes = [c_int]
+    dll.get_thread_count.restype = c_int
+    dll.get_thread_count.argtypes = []
+    ls_args = [c_int, c_int, _I, _I, _D, c_int, _D, c_int, _D, c_double, c_int, _D]
+    for name in ("cg_least_squares_from_python", "cg_least_squares2_from_python"):
+        getattr(dll, name).restype = c_int
+        getattr(dll, name).argtypes = ls_args
+    dll.als_from_python.restype = c_int
+    dll.als_from_python.argtypes = [_I, _I, c_int, _D, c_int, c_int, _D, c_int, _D, c_double,
+                                    c_int, c_int]
+    dll.mrb_last_error.restype = ctypes.c_char_p
+    dll.mrb_last_error.argtypes = []
+    dll.mrb_build_info.restype = ctypes.c_char_p
+    dll.mrb_build_info.argtypes = []
+    dll.mrb_device_count.restype = c_int
+    dll.mrb_device_count.argtypes = []
+    dll.mrb_group_by.restype = c_int
+    dll.mrb_group_by.argtypes = [_I, c_int, c_int, _I, _I]
+    dll.mrb_csr_transpose.restype = c_int
+    dll.mrb_csr_transpose.argtypes = [c_int, c_int, _I, _I, _D, _I, _I, _D]
+    dll.mrb_als_create.restype = c_int
+    dll.mrb_als_create.argtypes = [_I, _I, c_int, _D, c_int, c_int, c_int,
+                                   ctypes.POINTER(c_void_p)]
+    dll.mrb_als_set_factors.restype = c_int
+    dll.mrb_als_set_factors.argtypes = [c_void_p, _D, _D]
+    dll.mrb_als_get_factors.restype = c_int
+    dll.mrb_als_get_factors.argtypes = [c_void_p, _D, _D]
+    dll.mrb_als_get_index.restype = c_int
+    dll.mrb_als_get_index.argtypes = [c_void_p, _I, _I, _I, _I]
+    dll.mrb_als_run.restype = c_int
+    dll.mrb_als_run.argtypes = [c_void_p, c_int, c_double, c_int, ctypes.POINTER(AlsRunInfo)]
+    dll.mrb_als_destroy.restype = None
+    dll.mrb_als_destroy.argtypes = [c_void_p]
+    return dll
+
+
+def load(path=None):
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise ImportError(
+            "%s is missing: build it with `make -C movie_recommender_b200/csrc` "
+            "(there is no CPU fallback)" % path)
+    return _declare(ctypes.CDLL(path))
+
+
+dll = load()
+
+
+def check(code):
+    """Raise on a negative return code; pass the reference's iteration count through."""
+    if code < 0:
+        raise CppLsError(code, dll.mrb_last_error().decode("utf-8", "replace"))
+    return code
+
+
+def ip(a):
+    return a.ctypes.data_as(_I)
+
+
+def dp(a):
+    return a.ctypes.data_as(_D)

@@ -1,0 +1,202 @@
+"""Drop-in for the reference's ``python/full_data/cpp_ls.py`` (== ``cpp/python/cpp_ls.py``).
+
+Same functions, same arguments, same return values; the work is done by the CUDA library
+(``movie_recommender_b200/cpp_ls_lib.so``, include/cpp_ls_b200.h) instead of the reference's
+threaded C++ (``cpp/ls_lib``).  Differences, all deliberate:
+
+* ``cg_least_squares(..., algorithm != 1)`` works.  The reference calls the non-existent symbol
+  ``cg_least_squares_from_python2`` there (cpp_ls.py:106) and raises AttributeError; the real
+  export is ``cg_least_squares2_from_python`` (ls_linux_dll.cpp:54), which is what is called.
+* keyword-only extras that the reference does not have: explicit initial vectors (``x0``,
+  ``user_factors`` / ``item_factors``) so that a caller can be deterministic without touching
+  the global NumPy RNG; when they are omitted the initial vectors are drawn from the global
+  NumPy RNG with exactly the reference's calls (cpp_ls.py:92, :150-151).
+* ``algorithm`` accepts the extension values 3 and 4 for ``als`` (include/cpp_ls_b200.h).
+* a failing native call raises ``CppLsError`` instead of terminating the process.
+"""
+import ctypes
+import multiprocessing
+import random
+
+import numpy
+
+from . import _lib
+from ._lib import CppLsError  # noqa: F401  (re-export)
+
+_dll = _lib.dll
+
+
+def _load_dll():
+    # cpp_ls.py:5-14: the library is loaded at import time and told how many threads to use.
+    # Here the thread count selects the reference summation order to reproduce.
+    _dll.set_thread_count(multiprocessing.cpu_count())
+
+
+_load_dll()
+
+
+def has_dll_loaded():
+    """Returns true if the library has been successfully loaded (cpp_ls.py:23-36)."""
+    old_thread_count = _dll.get_thread_count()
+    random_number = random.randint(1, 100000)
+    _dll.set_thread_count(random_number)
+    success = _dll.get_thread_count() == random_number
+    _dll.set_thread_count(old_thread_count)
+    return success
+
+
+def set_thread_count(thread_count: int):
+    _dll.set_thread_count(thread_count)
+
+
+def get_thread_count():
+    return _dll.get_thread_count()
+
+
+def cg_least_squares(A_row_indices: numpy.ndarray, A_col_indices: numpy.ndarray,
+                     A_values: numpy.ndarray, A_num_columns: int, b: numpy.ndarray,
+                     min_r_decrease=0.01, max_iterations=200, algorithm=1, *, x0=None):
+    """Solves Ax = b in the least squares sense (cpp_ls.py:47-111).
+
+    :return: x, iterations, final_rr -- ``x`` is a numpy column vector of type double.
+    """
+    A_row_indices = numpy.ascontiguousarray(A_row_indices, dtype=numpy.int32)
+    A_col_indices = numpy.ascontiguousarray(A_col_indices, dtype=numpy.int32)
+    A_values = numpy.ascontiguousarray(A_values, dtype=numpy.double)
+    b = numpy.ascontiguousarray(b, dtype=numpy.double)
+    A_rows = len(A_row_indices) - 1
+    b_length = len(b)
+
+    # generate solution vector x (cpp_ls.py:92)
+    if x0 is None:
+        x = numpy.random.uniform(-1, 1, (A_num_columns, 1))
+    else:
+        x = numpy.array(x0, dtype=numpy.double).reshape(A_num_columns, 1)
+    x_length = A_num_columns
+
+    final_rr = ctypes.c_double(0)
+    fn = _dll.cg_least_squares_from_python if algorithm == 1 else _dll.cg_least_squares2_from_python
+    iterations = _lib.check(fn(
+        A_rows, A_num_columns, _lib.ip(A_row_indices), _lib.ip(A_col_indices), _lib.dp(A_values),
+        b_length, _lib.dp(b), x_length, _lib.dp(x), ctypes.c_double(min_r_decrease),
+        max_iterations, ctypes.cast(ctypes.byref(final_rr), _lib._D)))
+    return x, iterations, final_rr.value
+
+
+def als(user_ids: numpy.ndarray, item_ids: numpy.ndarray, ratings: numpy.ndarray,
+        num_item_factors: int, num_users: int, num_items: int, min_r_decrease=0.01,
+        max_iterations=200, algorithm=1, *, user_factors=None, item_factors=None):
+    """Derives user and item factors with ALS (cpp_ls.py:114-172).
+
+    :return: user_factors, item_factors, iterations -- flat float64 arrays of length
+        num_users*(num_item_factors+1) and num_items*num_item_factors.
+    """
+    user_ids = numpy.ascontiguousarray(user_ids, dtype=numpy.int32)
+    item_ids = numpy.ascontiguousarray(item_ids, dtype=numpy.int32)
+    ratings = numpy.ascontiguousarray(ratings, dtype=numpy.double)
+
+    # allocate "user_factors" and "item_factors" (cpp_ls.py:149-151)
+    num_user_factors = num_item_factors + 1
+    if user_factors is None:
+        user_factors = numpy.random.uniform(-1, 1, num_users * num_user_factors)
+    else:
+        user_factors = numpy.array(user_factors, dtype=numpy.double).reshape(-1)
+    if item_factors is None:
+        item_factors = numpy.random.uniform(-1, 1, num_items * num_item_factors)
+    else:
+        item_factors = numpy.array(item_factors, dtype=numpy.double).reshape(-1)
+    if len(user_factors) != num_users * num_user_factors or \
+            len(item_factors) != num_items * num_item_factors:
+        raise ValueError("initial factor arrays have the wrong length")
+
+    iterations = _lib.check(_dll.als_from_python(
+        _lib.ip(user_ids), _lib.ip(item_ids), len(ratings), _lib.dp(ratings), num_item_factors,
+        len(user_factors), _lib.dp(user_factors), len(item_factors), _lib.dp(item_factors),
+        ctypes.c_double(min_r_decrease), max_iterations, algorithm))
+    return user_factors, item_factors, iterations
+
+
+class AlsProblem:
+    """Device-resident ALS problem (extension; include/cpp_ls_b200.h section 4).
+
+    The COO ratings are uploaded and indexed once; factors live in HBM between ``run`` calls, so
+    a benchmark can time sweeps with no host traffic in the timed region.
+    """
+
+    def __init__(self, user_ids, item_ids, ratings, num_item_factors, num_users, num_items):
+        self._user_ids = numpy.ascontiguousarray(user_ids, dtype=numpy.int32)
+        self._item_ids = numpy.ascontiguousarray(item_ids, dtype=numpy.int32)
+        self._ratings = numpy.ascontiguousarray(ratings, dtype=numpy.double)
+        self.k, self.num_users, self.num_items = num_item_factors, num_users, num_items
+        self._h = ctypes.c_void_p()
+        _lib.check(_dll.mrb_als_create(
+            _lib.ip(self._user_ids), _lib.ip(self._item_ids), len(self._ratings),
+            _lib.dp(self._ratings), num_item_factors, num_users, num_items,
+            ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            _dll.mrb_als_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_factors(self, user_factors, item_factors):
+        uf = numpy.ascontiguousarray(user_factors, dtype=numpy.double).reshape(-1)
+        itf = numpy.ascontiguousarray(item_factors, dtype=numpy.double).reshape(-1)
+        assert len(uf) == self.num_users * (self.k + 1) and len(itf) == self.num_items * self.k
+        _lib.check(_dll.mrb_als_set_factors(self._h, _lib.dp(uf), _lib.dp(itf)))
+
+    def get_factors(self):
+        uf = numpy.empty(self.num_users * (self.k + 1), dtype=numpy.double)
+        itf = numpy.empty(self.num_items * self.k, dtype=numpy.double)
+        _lib.check(_dll.mrb_als_get_factors(self._h, _lib.dp(uf), _lib.dp(itf)))
+        return uf, itf
+
+    def get_index(self):
+        """(u_ptr, u_idx, i_ptr, i_idx): the stable groupings of rating positions (K4)."""
+        n = max(len(self._ratings), 1)
+        u_ptr = numpy.zeros(self.num_users + 1, dtype=numpy.int32)
+        i_ptr = numpy.zeros(self.num_items + 1, dtype=numpy.int32)
+        u_idx = numpy.zeros(n, dtype=numpy.int32)
+        i_idx = numpy.zeros(n, dtype=numpy.int32)
+        _lib.check(_dll.mrb_als_get_index(self._h, _lib.ip(u_ptr), _lib.ip(u_idx), _lib.ip(i_ptr),
+                                          _lib.ip(i_idx)))
+        m = len(self._ratings)
+        return u_ptr, u_idx[:m], i_ptr, i_idx[:m]
+
+    def run(self, algorithm=1, min_r_decrease=0.01, max_iterations=200):
+        """Runs the sweep loop on the device; returns the filled ``AlsRunInfo``."""
+        info = _lib.AlsRunInfo()
+        _lib.check(_dll.mrb_als_run(self._h, algorithm, ctypes.c_double(min_r_decrease),
+                                    max_iterations, ctypes.byref(info)))
+        return info
+
+
+def group_by(keys, num_groups):
+    """Stable grouping on the GPU (K4): returns (ptr[num_groups+1], idx[n])."""
+    keys = numpy.ascontiguousarray(keys, dtype=numpy.int32)
+    ptr = numpy.zeros(num_groups + 1, dtype=numpy.int32)
+    idx = numpy.zeros(max(len(keys), 1), dtype=numpy.int32)
+    _lib.check(_dll.mrb_group_by(_lib.ip(keys), len(keys), num_groups, _lib.ip(ptr), _lib.ip(idx)))
+    return ptr, idx[:len(keys)]
+
+
+def csr_transpose(rows, cols, rowptr, colidx, vals):
+    """Stable CSR -> CSC on the GPU (K4): returns (t_ptr, t_row, t_val)."""
+    rowptr = numpy.ascontiguousarray(rowptr, dtype=numpy.int32)
+    colidx = numpy.ascontiguousarray(colidx, dtype=numpy.int32)
+    vals = numpy.ascontiguousarray(vals, dtype=numpy.double)
+    nnz = int(rowptr[rows])
+    t_ptr = numpy.zeros(cols + 1, dtype=numpy.int32)
+    t_row = numpy.zeros(max(nnz, 1), dtype=numpy.int32)
+    t_val = numpy.zeros(max(nnz, 1), dtype=numpy.double)
+    _lib.check(_dll.mrb_csr_transpose(rows, cols, _lib.ip(rowptr), _lib.ip(colidx), _lib.dp(vals),
+                                      _lib.ip(t_ptr), _lib.ip(t_row), _lib.dp(t_val)))
+    return t_ptr, t_row[:nnz], t_val[:nnz]

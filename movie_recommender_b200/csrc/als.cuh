@@ -1,0 +1,71 @@
+// ALS training problem resident on one GPU (replaces als() of cpp/ls_lib/matrix.cpp:744-893).
+//
+// Data layout in HBM (all int32 / float64, as the reference's API):
+//   user_ids[nnz], item_ids[nnz], ratings[nnz]      COO in INPUT order (the reference's row order)
+//   u_ptr[nu+1], u_idx[nnz]                         stable grouping of rating positions by user
+//   i_ptr[ni+1], i_idx[nnz]                         stable grouping of rating positions by item
+//   user_factors[nu*(k+1)], item_factors[ni*k]      row-major, in/out (warm start)
+// The reference's materialised nnz x (k+1) matrices (17 GB each at ML-27M, k=50) never exist.
+#pragma once
+#include <memory>
+
+#include "common.cuh"
+#include "faithful_cg.cuh"
+
+namespace mrb {
+
+enum AlsAlgorithm : int {
+    ALS_REF_CG = 1,        // reference algorithm=1: cg_least_squares every sweep (bit-faithful)
+    ALS_REF_CG_T = 2,      // reference algorithm=2: explicit-transpose CG on sweep 0 (bit-faithful)
+    ALS_GRAM_CG = 3,       // same CG with global alpha/beta on per-row Gram blocks, GPU-native sums
+    ALS_GRAM_CHOLESKY = 4  // per-row normal equations solved exactly (in-shared-memory Cholesky)
+};
+
+struct AlsRunInfo {
+    int sweeps_returned = 0;   // the reference's return value (sweep counter at exit)
+    int sweeps_run = 0;        // number of (user, item) half-sweep pairs executed
+    int cg_iterations = 0;     // total inner CG iterations (CG modes)
+    double last_rr = 0;        // item-solve normal-equation residual of the last sweep
+    float device_ms = 0;       // CUDA-event time of the sweep loop on the problem's stream
+};
+
+class AlsProblem {
+public:
+    // Host pointers; uploads and builds both groupings (K4).
+    AlsProblem(const int* user_ids, const int* item_ids, int nnz, const double* ratings, int k,
+               int num_users, int num_items);
+    ~AlsProblem();
+
+    void set_factors(const double* user_factors, const double* item_factors);  // host -> device
+    void get_factors(double* user_factors, double* item_factors);              // device -> host
+
+    // Runs the sweep loop of matrix.cpp:814-890 on the device-resident problem.
+    AlsRunInfo run(int algorithm, double min_r_decrease, int max_iteration, int thread_count);
+
+    int nnz() const { return nnz_; }
+    int k() const { return k_; }
+    int num_users() const { return nu_; }
+    int num_items() const { return ni_; }
+    cudaStream_t stream() const { return s_; }
+    const int* u_ptr() const { return u_ptr_.p; }
+    const int* u_idx() const { return u_idx_.p; }
+    const int* i_ptr() const { return i_ptr_.p; }
+    const int* i_idx() const { return i_idx_.p; }
+    double* user_factors() { return uf_.p; }
+    double* item_factors() { return itf_.p; }
+    float index_build_ms() const { return index_ms_; }
+
+private:
+    AlsRunInfo run_faithful(int algorithm, double min_r_decrease, int max_iteration, int T);
+    AlsRunInfo run_gram(int algorithm, double min_r_decrease, int max_iteration);
+
+    int nnz_, k_, nu_, ni_;
+    cudaStream_t s_ = nullptr;
+    DevBuf<int> user_ids_, item_ids_, u_ptr_, u_idx_, i_ptr_, i_idx_;
+    DevBuf<double> ratings_, uf_, itf_, rmb_;
+    float index_ms_ = 0;
+    struct GramState;
+    std::shared_ptr<GramState> gram_;  // shared_ptr: deleter bound where GramState is complete (als_gram.cu)
+};
+
+}  // namespace mrb

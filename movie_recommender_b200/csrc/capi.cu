@@ -1,0 +1,236 @@
+// C ABI (include/cpp_ls_b200.h).  Section 1 replaces cpp/ls_lib/ls_linux_dll.cpp:8-103.
+#include "../../include/cpp_ls_b200.h"
+
+#include <cstring>
+#include <vector>
+
+#include "als.cuh"
+#include "common.cuh"
+#include "faithful_cg.cuh"
+#include "index_build.cuh"
+
+namespace mrb {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+template <typename F>
+static int guarded(F&& body) {
+    try {
+        return body();
+    } catch (const Error& e) {
+        set_last_error(e.what());
+        cudaGetLastError();  // clear a sticky launch-configuration error, if any
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        set_last_error("host allocation failed");
+        return kErrInternal;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return kErrInternal;
+    }
+}
+
+// ls_linux_dll.cpp:6
+static int g_thread_count = 4;
+
+static int solve_ls(int variant, int A_rows, int A_cols, const int* rowptr, const int* colidx,
+                    const double* vals, int b_length, const double* b, int x_length, double* x,
+                    double min_r_decrease, int max_iteration, double* final_rr) {
+    // the reference throws on these (matrix.cpp:403-405, 422-424)
+    MRB_REQUIRE(A_rows >= 0 && A_cols >= 0, "cg_least_squares: negative dimension");
+    MRB_REQUIRE(b_length == A_rows, "cg_least_squares: len(b) != rows of A");
+    MRB_REQUIRE(x_length == A_cols, "cg_least_squares: len(x) != columns of A");
+    const int nnz = rowptr[A_rows];
+    MRB_REQUIRE(nnz >= 0, "cg_least_squares: negative nnz");
+    cudaStream_t s;
+    MRB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{s};
+    DevBuf<int> d_rowptr(static_cast<size_t>(A_rows) + 1), d_col(nnz);
+    DevBuf<double> d_vals(nnz), d_b(A_rows), d_x(A_cols);
+    d_rowptr.upload(rowptr, static_cast<size_t>(A_rows) + 1, s);
+    d_col.upload(colidx, nnz, s);
+    d_vals.upload(vals, nnz, s);
+    d_b.upload(b, A_rows, s);
+    d_x.upload(x, A_cols, s);
+    CsrFaithfulOp op(A_rows, A_cols, nnz, d_rowptr.p, d_col.p, d_vals.p, s);
+    FaithfulCG cg(A_rows, A_cols, g_thread_count, s);
+    CgResult r = cg.solve(op, d_b.p, d_x.p, min_r_decrease, max_iteration, variant);
+    d_x.download(x, A_cols, s);
+    MRB_CUDA(cudaStreamSynchronize(s));
+    if (final_rr) *final_rr = r.final_rr;
+    return r.iterations;
+}
+}  // namespace mrb
+
+using namespace mrb;
+
+extern "C" {
+
+void set_thread_count(int thread_count) { g_thread_count = thread_count; }
+int get_thread_count(void) { return g_thread_count; }
+
+int cg_least_squares_from_python(int A_rows, int A_cols, int* A_row_indices, int* A_col_indices,
+                                 double* A_values, int b_length, double* b_values, int x_length,
+                                 double* x_values, double min_r_decrease, int max_iteration,
+                                 double* final_rr) {
+    return guarded([&] {
+        return solve_ls(1, A_rows, A_cols, A_row_indices, A_col_indices, A_values, b_length,
+                        b_values, x_length, x_values, min_r_decrease, max_iteration, final_rr);
+    });
+}
+
+int cg_least_squares2_from_python(int A_rows, int A_cols, int* A_row_indices, int* A_col_indices,
+                                  double* A_values, int b_length, double* b_values, int x_length,
+                                  double* x_values, double min_r_decrease, int max_iteration,
+                                  double* final_rr) {
+    return guarded([&] {
+        return solve_ls(2, A_rows, A_cols, A_row_indices, A_col_indices, A_values, b_length,
+                        b_values, x_length, x_values, min_r_decrease, max_iteration, final_rr);
+    });
+}
+
+int als_from_python(int* user_ids, int* item_ids, int ratings_length, double* ratings_values,
+                    int num_item_factors, int user_factors_length, double* user_factors_values,
+                    int item_factors_length, double* item_factors_values, double min_r_decrease,
+                    int max_iteration, int algorithm) {
+    return guarded([&] {
+        const int k = num_item_factors;
+        MRB_REQUIRE(k >= 1, "als: num_item_factors must be >= 1");
+        MRB_REQUIRE(user_factors_length % (k + 1) == 0,
+                    "als: len(user_factors) is not a multiple of num_item_factors + 1");
+        MRB_REQUIRE(item_factors_length % k == 0,
+                    "als: len(item_factors) is not a multiple of num_item_factors");
+        AlsProblem p(user_ids, item_ids, ratings_length, ratings_values, k,
+                     user_factors_length / (k + 1), item_factors_length / k);
+        p.set_factors(user_factors_values, item_factors_values);
+        AlsRunInfo info = p.run(algorithm, min_r_decrease, max_iteration, g_thread_count);
+        p.get_factors(user_factors_values, item_factors_values);
+        return info.sweeps_returned;
+    });
+}
+
+const char* mrb_last_error(void) { return g_last_error.c_str(); }
+
+int mrb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* mrb_build_info(void) {
+    return "movie_recommender_b200 cpp_ls_lib: CUDA sm_100a, fp64, built " __DATE__;
+}
+
+int mrb_group_by(const int* keys, int n, int num_groups, int* ptr_out, int* idx_out) {
+    return guarded([&] {
+        MRB_REQUIRE(n >= 0 && num_groups >= 0, "mrb_group_by: negative size");
+        cudaStream_t s;
+        MRB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{s};
+        DevBuf<int> d_keys(n), d_ptr(static_cast<size_t>(num_groups) + 1), d_idx(n);
+        d_keys.upload(keys, n, s);
+        stable_group_by(d_keys.p, n, num_groups, d_ptr.p, d_idx.p, s);
+        d_ptr.download(ptr_out, static_cast<size_t>(num_groups) + 1, s);
+        d_idx.download(idx_out, n, s);
+        MRB_CUDA(cudaStreamSynchronize(s));
+        return 0;
+    });
+}
+
+int mrb_csr_transpose(int rows, int cols, const int* rowptr, const int* colidx, const double* vals,
+                      int* t_ptr, int* t_row, double* t_val) {
+    return guarded([&] {
+        MRB_REQUIRE(rows >= 0 && cols >= 0, "mrb_csr_transpose: negative size");
+        const int nnz = rowptr[rows];
+        cudaStream_t s;
+        MRB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{s};
+        DevBuf<int> d_rowptr(static_cast<size_t>(rows) + 1), d_col(nnz);
+        DevBuf<double> d_vals(nnz);
+        DevBuf<int> d_tptr(static_cast<size_t>(cols) + 1), d_trow(nnz);
+        DevBuf<double> d_tval(nnz);
+        d_rowptr.upload(rowptr, static_cast<size_t>(rows) + 1, s);
+        d_col.upload(colidx, nnz, s);
+        d_vals.upload(vals, nnz, s);
+        csr_transpose(rows, cols, nnz, d_rowptr.p, d_col.p, d_vals.p, d_tptr.p, d_trow.p, d_tval.p, s);
+        d_tptr.download(t_ptr, static_cast<size_t>(cols) + 1, s);
+        d_trow.download(t_row, nnz, s);
+        d_tval.download(t_val, nnz, s);
+        MRB_CUDA(cudaStreamSynchronize(s));
+        return 0;
+    });
+}
+
+struct mrb_als_problem {
+    AlsProblem impl;
+    mrb_als_problem(const int* u, const int* i, int nnz, const double* r, int k, int nu, int ni)
+        : impl(u, i, nnz, r, k, nu, ni) {}
+};
+
+int mrb_als_create(const int* user_ids, const int* item_ids, int num_ratings,
+                   const double* ratings, int num_item_factors, int num_users, int num_items,
+                   mrb_als_problem** out) {
+    return guarded([&] {
+        MRB_REQUIRE(out != nullptr, "mrb_als_create: null out");
+        *out = new mrb_als_problem(user_ids, item_ids, num_ratings, ratings, num_item_factors,
+                                   num_users, num_items);
+        return 0;
+    });
+}
+
+int mrb_als_set_factors(mrb_als_problem* p, const double* user_factors, const double* item_factors) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        p->impl.set_factors(user_factors, item_factors);
+        return 0;
+    });
+}
+
+int mrb_als_get_factors(mrb_als_problem* p, double* user_factors, double* item_factors) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        p->impl.get_factors(user_factors, item_factors);
+        return 0;
+    });
+}
+
+int mrb_als_get_index(mrb_als_problem* p, int* u_ptr, int* u_idx, int* i_ptr, int* i_idx) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        AlsProblem& a = p->impl;
+        cudaStream_t s = a.stream();
+        const size_t nnz = static_cast<size_t>(a.nnz());
+        MRB_CUDA(cudaMemcpyAsync(u_ptr, a.u_ptr(), sizeof(int) * (a.num_users() + 1ull), cudaMemcpyDeviceToHost, s));
+        MRB_CUDA(cudaMemcpyAsync(i_ptr, a.i_ptr(), sizeof(int) * (a.num_items() + 1ull), cudaMemcpyDeviceToHost, s));
+        if (nnz) {
+            MRB_CUDA(cudaMemcpyAsync(u_idx, a.u_idx(), sizeof(int) * nnz, cudaMemcpyDeviceToHost, s));
+            MRB_CUDA(cudaMemcpyAsync(i_idx, a.i_idx(), sizeof(int) * nnz, cudaMemcpyDeviceToHost, s));
+        }
+        MRB_CUDA(cudaStreamSynchronize(s));
+        return 0;
+    });
+}
+
+int mrb_als_run(mrb_als_problem* p, int algorithm, double min_r_decrease, int max_iteration,
+                mrb_als_run_info* info) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        AlsRunInfo r = p->impl.run(algorithm, min_r_decrease, max_iteration, g_thread_count);
+        if (info) {
+            info->sweeps_returned = r.sweeps_returned;
+            info->sweeps_run = r.sweeps_run;
+            info->cg_iterations = r.cg_iterations;
+            info->last_rr = r.last_rr;
+            info->device_ms = r.device_ms;
+            info->index_build_ms = p->impl.index_build_ms();
+        }
+        return r.sweeps_returned;
+    });
+}
+
+void mrb_als_destroy(mrb_als_problem* p) { delete p; }
+
+}  // extern "C"

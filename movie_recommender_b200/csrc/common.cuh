@@ -1,0 +1,113 @@
+// Common plumbing for the B200 (sm_100a) least-squares / ALS library: error handling, device
+// buffers, exact-rounding arithmetic helpers.  No torch types anywhere in this library.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+namespace mrb {
+
+// Error codes returned through the C ABI (never on a success path; the reference's functions
+// return iteration counts >= 0, cpp/ls_lib/ls_linux_dll.cpp:28-103).
+// (values mirror the MRB_ERR_* macros of include/cpp_ls_b200.h)
+enum : int {
+    kErrCuda = -1,       // a CUDA runtime call failed (no device, OOM, launch failure ...)
+    kErrArgument = -2,   // dimension mismatch / unsupported size (the reference throws)
+    kErrInternal = -3,
+};
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& msg);
+
+#define MRB_CUDA(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            throw ::mrb::Error(::mrb::kErrCuda, std::string(#expr) + " failed at " +   \
+                                                        __FILE__ + ":" +                   \
+                                                        std::to_string(__LINE__) + ": " +  \
+                                                        cudaGetErrorString(e__));          \
+    } while (0)
+
+#define MRB_REQUIRE(cond, msg)                                            \
+    do {                                                                  \
+        if (!(cond)) throw ::mrb::Error(::mrb::kErrArgument, (msg));  \
+    } while (0)
+
+// RAII device allocation.
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) MRB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void upload(const T* host, size_t count, cudaStream_t s) {
+        if (count) MRB_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T* host, size_t count, cudaStream_t s) const {
+        if (count) MRB_CUDA(cudaMemcpyAsync(host, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+};
+
+// RAII pinned host allocation (small status words read back every CG batch).
+template <typename T>
+struct PinnedBuf {
+    T* p = nullptr;
+    explicit PinnedBuf(size_t count) { MRB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p), count * sizeof(T))); }
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+
+inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+// The reference's chunk boundary formula, evaluated in FLOAT32 exactly as
+// cpp/ls_lib/matrix.cpp:12 / :180 / :639 / :768 do: (int)(((float)i) / T * len).
+inline void chunk_table(int T, int len, int* bounds /* T+1 */) {
+    bounds[0] = 0;
+    for (int i = 1; i < T; i++) {
+        volatile float q = static_cast<float>(i) / static_cast<float>(T);
+        volatile float f = q * static_cast<float>(len);
+        bounds[i] = static_cast<int>(f);
+    }
+    bounds[T] = len;
+}
+
+#ifdef __CUDACC__
+// Separately rounded multiply / add: the reference is compiled for baseline x86-64 (no FMA), so
+// bit-faithful kernels must never contract a*b+c.
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+
+__device__ __forceinline__ double shfl_double(double v, int src) {
+    return __shfl_sync(0xffffffffu, v, src);
+}
+#endif
+
+}  // namespace mrb

@@ -1,0 +1,431 @@
+// Reference-order conjugate gradient (see faithful_cg.cuh for the contract).
+#include "faithful_cg.cuh"
+
+#include <climits>
+
+#include "index_build.cuh"
+
+namespace mrb {
+
+using State = FaithfulCG::State;
+
+// ------------------------------------------------------------------------------------------
+// Dots: one CTA per reference chunk.  Warps 1..3 stream a[i]*b[i] (separately rounded) into a
+// double-buffered shared tile; lane 0 of warp 0 adds the tile in index order.  The chain of
+// dependent adds IS the reference's semantics (matrix.cpp:97-99) -- it cannot be split.
+// ------------------------------------------------------------------------------------------
+namespace {
+constexpr int DOT_THREADS = 128;
+constexpr int DOT_TILE = 1536;
+
+__global__ void __launch_bounds__(DOT_THREADS)
+k_dot_partials(const double* __restrict__ a, const double* __restrict__ b,
+               const int* __restrict__ bounds, double* __restrict__ partials,
+               const State* __restrict__ guard) {
+    if (guard && guard->done) return;
+    __shared__ double buf[2][DOT_TILE];
+    const int beg = bounds[blockIdx.x], end = bounds[blockIdx.x + 1];
+    const int len = end - beg;
+    const int ntiles = (len + DOT_TILE - 1) / DOT_TILE;
+    const int tid = threadIdx.x;
+    auto fill = [&](int tile, int which) {
+        if (tid < 32) return;
+        const int off = beg + tile * DOT_TILE;
+        for (int i = tid - 32; i < DOT_TILE; i += DOT_THREADS - 32) {
+            const int idx = off + i;
+            if (idx < end) buf[which][i] = xmul(a[idx], b[idx]);
+        }
+    };
+    double s = 0;
+    if (ntiles > 0) fill(0, 0);
+    __syncthreads();
+    for (int t = 0; t < ntiles; t++) {
+        if (t + 1 < ntiles) fill(t + 1, (t + 1) & 1);
+        if (tid == 0) {
+            const int cnt = min(DOT_TILE, len - t * DOT_TILE);
+            const double* src = buf[t & 1];
+            int i = 0;
+            for (; i + 8 <= cnt; i += 8) {
+                const double v0 = src[i], v1 = src[i + 1], v2 = src[i + 2], v3 = src[i + 3];
+                const double v4 = src[i + 4], v5 = src[i + 5], v6 = src[i + 6], v7 = src[i + 7];
+                s = xadd(s, v0); s = xadd(s, v1); s = xadd(s, v2); s = xadd(s, v3);
+                s = xadd(s, v4); s = xadd(s, v5); s = xadd(s, v6); s = xadd(s, v7);
+            }
+            for (; i < cnt; i++) s = xadd(s, src[i]);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) partials[blockIdx.x] = s;
+}
+
+__device__ __forceinline__ double merge_partials(const double* partials, int T) {
+    double total = 0;  // matrix.cpp:388-391
+    for (int t = 0; t < T; t++) total = xadd(total, partials[t]);
+    return total;
+}
+
+__global__ void k_cg_init(State* st, const double* partials, int T, double min_r_decrease,
+                          int max_it) {
+    const double rr = merge_partials(partials, T);  // matrix.cpp:485
+    st->rr = rr;
+    st->final_rr = rr;
+    st->alpha = 0;
+    st->beta = 0;
+    st->one_minus_mrd = 1 - min_r_decrease;
+    st->it = 0;
+    st->slow = 0;
+    st->max_it = max_it;
+    st->done = (max_it <= 0 || rr < 1e-6) ? 2 : 0;  // matrix.cpp:488, :490
+}
+
+__global__ void k_cg_alpha(State* st, const double* partials, int T) {
+    if (st->done) return;
+    const double pAp = merge_partials(partials, T);  // matrix.cpp:497
+    st->alpha = st->rr / pAp;                        // :498
+}
+
+__global__ void k_cg_beta(State* st, const double* partials, int T) {
+    if (st->done) return;
+    const double rr2 = merge_partials(partials, T);  // matrix.cpp:507
+    st->final_rr = rr2;
+    const double beta = rr2 / st->rr;                // :510
+    st->beta = beta;
+    if (beta > st->one_minus_mrd) st->slow++; else st->slow = 0;  // :513-516
+    if (st->slow >= 2) { st->done = 1; return; }     // :518, iteration not incremented
+    st->rr = rr2;
+    st->it++;
+    // loop head of the next iteration (:488, :490); the skipped p update is not observable
+    if (st->it >= st->max_it || rr2 < 1e-6) st->done = 2;
+}
+
+__global__ void k_residual_init(const double* __restrict__ Ap, const double* __restrict__ b2,
+                                double* __restrict__ r, double* __restrict__ p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ri = xadd(xmul(1.0, Ap[i]), xmul(-1.0, b2[i]));  // matrix.cpp:472
+    r[i] = ri;
+    p[i] = xmul(ri, -1.0);                                        // :476
+}
+
+__global__ void k_update_xr(const State* __restrict__ st, double* __restrict__ x,
+                            double* __restrict__ r, const double* __restrict__ p,
+                            const double* __restrict__ Ap, int n) {
+    if (st->done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double alpha = st->alpha;
+    x[i] = xadd(xmul(1.0, x[i]), xmul(alpha, p[i]));   // matrix.cpp:501
+    r[i] = xadd(xmul(1.0, r[i]), xmul(alpha, Ap[i]));  // :504
+}
+
+__global__ void k_update_p(const State* __restrict__ st, const double* __restrict__ r,
+                           double* __restrict__ p, int n) {
+    if (st->done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    p[i] = xadd(xmul(-1.0, r[i]), xmul(st->beta, p[i]));  // matrix.cpp:521
+}
+}  // namespace
+
+FaithfulCG::FaithfulCG(int rows, int cols, int thread_count, cudaStream_t s)
+    : rows_(rows), cols_(cols), T_(thread_count < 1 ? 1 : thread_count), s_(s),
+      b2_(cols), r_(cols), Ap_(cols), p_(cols), tmp_(rows), partials_(T_),
+      row_bounds_(T_ + 1), col_bounds_(T_ + 1), one_chunk_(2), state_(1), host_state_(1) {
+    std::vector<int> bd(T_ + 1);
+    chunk_table(T_, rows_, bd.data());
+    MRB_CUDA(cudaMemcpyAsync(row_bounds_.p, bd.data(), sizeof(int) * (T_ + 1),
+                             cudaMemcpyHostToDevice, s_));
+    MRB_CUDA(cudaStreamSynchronize(s_));
+    chunk_table(T_, cols_, bd.data());
+    MRB_CUDA(cudaMemcpyAsync(col_bounds_.p, bd.data(), sizeof(int) * (T_ + 1),
+                             cudaMemcpyHostToDevice, s_));
+    const int one[2] = {0, rows_};
+    MRB_CUDA(cudaMemcpyAsync(one_chunk_.p, one, sizeof(one), cudaMemcpyHostToDevice, s_));
+    MRB_CUDA(cudaStreamSynchronize(s_));
+}
+
+CgResult FaithfulCG::solve(FaithfulOp& A, const double* d_b, double* d_x, double min_r_decrease,
+                           int max_iteration, int variant) {
+    MRB_REQUIRE(A.rows == rows_ && A.cols == cols_, "FaithfulCG: operator shape mismatch");
+    const int* bounds = variant == 1 ? row_bounds_.p : one_chunk_.p;
+    const int nchunks = variant == 1 ? T_ : 1;
+    const int vb = ceil_div(cols_ > 0 ? cols_ : 1, 256);
+    State* st = state_.p;
+
+    A.tmul(d_b, b2_.p, bounds, nchunks, s_);       // b2 = A^T b      (matrix.cpp:465 / :549)
+    A.mul(d_x, tmp_.p, s_);                        // tmp = A x       (:469)
+    A.tmul(tmp_.p, Ap_.p, bounds, nchunks, s_);    // Ap = A^T tmp    (:470)
+    k_residual_init<<<vb, 256, 0, s_>>>(Ap_.p, b2_.p, r_.p, p_.p, cols_);
+    k_dot_partials<<<T_, DOT_THREADS, 0, s_>>>(r_.p, r_.p, col_bounds_.p, partials_.p, nullptr);
+    k_cg_init<<<1, 1, 0, s_>>>(st, partials_.p, T_, min_r_decrease, max_iteration);
+    MRB_CUDA(cudaGetLastError());
+
+    // Iterations are enqueued in small batches; every kernel is a no-op once `done` is set on
+    // the device, so the host only needs to look at the state once per batch.
+    const int batch = 4;
+    A.guard = &st->done;
+    for (;;) {
+        MRB_CUDA(cudaMemcpyAsync(host_state_.p, st, sizeof(State), cudaMemcpyDeviceToHost, s_));
+        MRB_CUDA(cudaStreamSynchronize(s_));
+        if (host_state_.p->done) break;
+        for (int i = 0; i < batch; i++) {
+            A.mul(p_.p, tmp_.p, s_);                        // :493
+            A.tmul(tmp_.p, Ap_.p, bounds, nchunks, s_);     // :494
+            k_dot_partials<<<T_, DOT_THREADS, 0, s_>>>(p_.p, Ap_.p, col_bounds_.p, partials_.p, st);
+            k_cg_alpha<<<1, 1, 0, s_>>>(st, partials_.p, T_);
+            k_update_xr<<<vb, 256, 0, s_>>>(st, d_x, r_.p, p_.p, Ap_.p, cols_);
+            k_dot_partials<<<T_, DOT_THREADS, 0, s_>>>(r_.p, r_.p, col_bounds_.p, partials_.p, st);
+            k_cg_beta<<<1, 1, 0, s_>>>(st, partials_.p, T_);
+            k_update_p<<<vb, 256, 0, s_>>>(st, r_.p, p_.p, cols_);
+        }
+        MRB_CUDA(cudaGetLastError());
+    }
+    A.guard = nullptr;
+    CgResult res;
+    res.iterations = host_state_.p->it;
+    res.final_rr = host_state_.p->final_rr;
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic CSR operator.
+// ------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_csr_mul(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                          const double* __restrict__ vals, const double* __restrict__ x,
+                          double* __restrict__ y, int rows, const int* __restrict__ guard) {
+    if (guard && *guard) return;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    double s = 0;
+    const int end = rowptr[r + 1];
+    for (int e = rowptr[r]; e < end; e++) s = xadd(s, xmul(vals[e], x[colidx[e]]));  // :203-209
+    y[r] = s;
+}
+
+// One warp per column of A.  32 entries are fetched and multiplied in parallel; the running
+// sum is then advanced entry by entry (every lane carries the same chain), folding the partial
+// into the total whenever the row index crosses a reference chunk boundary.
+__global__ void __launch_bounds__(256)
+k_csc_tmul(const int* __restrict__ t_ptr, const int* __restrict__ t_row,
+           const double* __restrict__ t_val, const double* __restrict__ t, double* __restrict__ y,
+           int cols, const int* __restrict__ bounds, const int* __restrict__ guard) {
+    if (guard && *guard) return;
+    const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (col >= cols) return;
+    const int lane = threadIdx.x & 31;
+    const int beg = t_ptr[col], end = t_ptr[col + 1];
+    double acc = 0, tot = 0;
+    int c = 0, next = bounds[1];
+    for (int e0 = beg; e0 < end; e0 += 32) {
+        const int e = e0 + lane;
+        int row_l = INT_MAX;
+        double prod_l = 0;
+        if (e < end) {
+            row_l = t_row[e];
+            prod_l = xmul(t[row_l], t_val[e]);  // matrix.cpp:244 (c_i * values[j])
+        }
+        const int cnt = min(32, end - e0);
+        for (int i = 0; i < cnt; i++) {
+            const int row = __shfl_sync(0xffffffffu, row_l, i);
+            const double prod = shfl_double(prod_l, i);
+            if (row >= next) {  // next reference thread's private vector (matrix.cpp:426-448)
+                tot = xadd(tot, acc);
+                acc = 0;
+                while (row >= bounds[c + 1]) c++;
+                next = bounds[c + 1];
+            }
+            acc = xadd(acc, prod);
+        }
+    }
+    tot = xadd(tot, acc);
+    if (lane == 0) y[col] = tot;
+}
+}  // namespace
+
+CsrFaithfulOp::CsrFaithfulOp(int rows_in, int cols_in, int nnz, const int* d_rowptr,
+                             const int* d_colidx, const double* d_vals, cudaStream_t s)
+    : nnz_(nnz), rowptr_(d_rowptr), colidx_(d_colidx), vals_(d_vals),
+      t_ptr_(static_cast<size_t>(cols_in) + 1), t_row_(nnz), t_val_(nnz) {
+    rows = rows_in;
+    cols = cols_in;
+    csr_transpose(rows, cols, nnz, d_rowptr, d_colidx, d_vals, t_ptr_.p, t_row_.p, t_val_.p, s);
+}
+
+void CsrFaithfulOp::mul(const double* d_x, double* d_y, cudaStream_t s) {
+    if (rows == 0) return;
+    k_csr_mul<<<ceil_div(rows, 256), 256, 0, s>>>(rowptr_, colidx_, vals_, d_x, d_y, rows, guard);
+}
+
+void CsrFaithfulOp::tmul(const double* d_t, double* d_y, const int* d_row_bounds, int /*nchunks*/,
+                         cudaStream_t s) {
+    if (cols == 0) return;
+    k_csc_tmul<<<ceil_div(static_cast<long long>(cols) * 32, 256), 256, 0, s>>>(
+        t_ptr_.p, t_row_.p, t_val_.p, d_t, d_y, cols, d_row_bounds, guard);
+}
+
+// ------------------------------------------------------------------------------------------
+// Implicit ALS operator.
+// ------------------------------------------------------------------------------------------
+namespace {
+constexpr int AM_WARPS = 8;   // warps per CTA in k_als_mul
+constexpr int AM_JCH = 32;    // unknowns staged per pass
+constexpr int AM_PS = AM_JCH + 1;  // odd row stride (doubles): conflict-free column walks
+
+// y[r] = sum_j A[r,j] * x[owner_r*width + j], j ascending, sequential from 0.
+// A warp takes 32 consecutive ratings: all lanes cooperate to fetch each rating's two rows
+// (coalesced) and store the separately rounded products in shared memory; lane i then adds
+// rating i's products in order.
+__global__ void __launch_bounds__(AM_WARPS * 32)
+k_als_mul(const int* __restrict__ owner, const int* __restrict__ other,
+          const double* __restrict__ other_f, const double* __restrict__ x,
+          double* __restrict__ y, int rows, int width, int other_stride, int k,
+          const int* __restrict__ guard) {
+    if (guard && *guard) return;
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* P = sm + static_cast<size_t>(w) * 32 * AM_PS;
+    const long long base = (static_cast<long long>(blockIdx.x) * AM_WARPS + w) * 32;
+    if (base >= rows) return;
+    const long long my_r = base + lane;
+    const bool valid = my_r < rows;
+    const int own_l = valid ? owner[my_r] : 0;
+    const int oth_l = valid ? other[my_r] : 0;
+    const int cnt = static_cast<int>(min(32LL, rows - base));
+    double s = 0;
+    for (int j0 = 0; j0 < width; j0 += AM_JCH) {
+        const int jn = min(AM_JCH, width - j0);
+        const int j = j0 + lane;
+#pragma unroll 4
+        for (int i = 0; i < cnt; i++) {
+            const int own = __shfl_sync(0xffffffffu, own_l, i);
+            const int oth = __shfl_sync(0xffffffffu, oth_l, i);
+            if (lane < jn) {
+                const double a = j < k ? other_f[static_cast<size_t>(oth) * other_stride + j] : 1.0;
+                P[i * AM_PS + lane] = xmul(a, x[static_cast<size_t>(own) * width + j]);  // :208
+            }
+        }
+        __syncwarp();
+        if (valid) {
+            const double* mine = P + lane * AM_PS;
+            for (int jj = 0; jj < jn; jj++) s = xadd(s, mine[jj]);
+        }
+        __syncwarp();
+    }
+    if (valid) y[my_r] = s;
+}
+
+// y[o*width + j] = chunk-folded sum over o's ratings (input order) of t[r] * A[r,j].
+// One warp per owner; lane l owns unknowns j = l, l+32, ...
+template <int JPL>
+__global__ void __launch_bounds__(256)
+k_als_tmul(const int* __restrict__ grp_ptr, const int* __restrict__ grp_idx,
+           const int* __restrict__ other, const double* __restrict__ other_f,
+           const double* __restrict__ t, double* __restrict__ y, int owners, int width,
+           int other_stride, int k, const int* __restrict__ bounds,
+           const int* __restrict__ guard) {
+    if (guard && *guard) return;
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (o >= owners) return;
+    const int lane = threadIdx.x & 31;
+    const int beg = grp_ptr[o], end = grp_ptr[o + 1];
+    double acc[JPL], tot[JPL];
+#pragma unroll
+    for (int m = 0; m < JPL; m++) { acc[m] = 0; tot[m] = 0; }
+    int c = 0, next = bounds[1];
+    for (int e0 = beg; e0 < end; e0 += 32) {
+        const int e = e0 + lane;
+        int r_l = INT_MAX, oth_l = 0;
+        double t_l = 0;
+        if (e < end) {
+            r_l = grp_idx[e];
+            oth_l = other[r_l];
+            t_l = t[r_l];
+        }
+        const int cnt = min(32, end - e0);
+        for (int i0 = 0; i0 < cnt; i0 += 4) {
+            double a[4][JPL];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int oth = __shfl_sync(0xffffffffu, oth_l, (i0 + u) & 31);
+#pragma unroll
+                for (int m = 0; m < JPL; m++) {
+                    const int j = lane + 32 * m;
+                    a[u][m] = (i0 + u < cnt && j < k)
+                                  ? other_f[static_cast<size_t>(oth) * other_stride + j]
+                                  : 1.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int r = __shfl_sync(0xffffffffu, r_l, (i0 + u) & 31);
+                const double tv = shfl_double(t_l, (i0 + u) & 31);
+                if (i0 + u < cnt) {
+                    if (r >= next) {  // matrix.cpp:426-448: next thread's private vector
+#pragma unroll
+                        for (int m = 0; m < JPL; m++) { tot[m] = xadd(tot[m], acc[m]); acc[m] = 0; }
+                        while (r >= bounds[c + 1]) c++;
+                        next = bounds[c + 1];
+                    }
+#pragma unroll
+                    for (int m = 0; m < JPL; m++) acc[m] = xadd(acc[m], xmul(tv, a[u][m]));  // :244
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < JPL; m++) {
+        const int j = lane + 32 * m;
+        if (j < width) y[static_cast<size_t>(o) * width + j] = xadd(tot[m], acc[m]);
+    }
+}
+}  // namespace
+
+AlsFaithfulOp::AlsFaithfulOp(int num_ratings, int num_owners, const int* d_owner,
+                             const int* d_other, const int* d_grp_ptr, const int* d_grp_idx,
+                             const double* d_other_f, int width, int other_stride, int k,
+                             bool has_one)
+    : owners_(num_owners), owner_(d_owner), other_(d_other), grp_ptr_(d_grp_ptr),
+      grp_idx_(d_grp_idx), other_f_(d_other_f), width_(width), other_stride_(other_stride),
+      k_(k), has_one_(has_one) {
+    rows = num_ratings;
+    cols = num_owners * width;
+    MRB_REQUIRE(width == k + (has_one ? 1 : 0), "AlsFaithfulOp: width/k mismatch");
+    MRB_REQUIRE(width <= 256, "ALS rank above 255 is not supported by the reference-order path");
+}
+
+void AlsFaithfulOp::mul(const double* d_x, double* d_y, cudaStream_t s) {
+    if (rows == 0) return;
+    static bool attr_set = false;
+    const size_t smem = sizeof(double) * AM_WARPS * 32 * AM_PS;
+    if (!attr_set) {
+        MRB_CUDA(cudaFuncSetAttribute(k_als_mul, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+        attr_set = true;
+    }
+    k_als_mul<<<ceil_div(rows, AM_WARPS * 32), AM_WARPS * 32, smem, s>>>(
+        owner_, other_, other_f_, d_x, d_y, rows, width_, other_stride_, k_, guard);
+}
+
+void AlsFaithfulOp::tmul(const double* d_t, double* d_y, const int* d_row_bounds, int /*nchunks*/,
+                         cudaStream_t s) {
+    if (owners_ == 0) return;
+    const int grid = ceil_div(static_cast<long long>(owners_) * 32, 256);
+    const int jpl = (width_ + 31) / 32;
+#define MRB_TMUL(J)                                                                         \
+    k_als_tmul<J><<<grid, 256, 0, s>>>(grp_ptr_, grp_idx_, other_, other_f_, d_t, d_y, owners_, \
+                                        width_, other_stride_, k_, d_row_bounds, guard)
+    switch (jpl) {
+        case 1: MRB_TMUL(1); break;
+        case 2: MRB_TMUL(2); break;
+        case 3: MRB_TMUL(3); break;
+        case 4: MRB_TMUL(4); break;
+        case 5: MRB_TMUL(5); break;
+        case 6: MRB_TMUL(6); break;
+        case 7: MRB_TMUL(7); break;
+        default: MRB_TMUL(8); break;
+    }
+#undef MRB_TMUL
+}
+
+}  // namespace mrb

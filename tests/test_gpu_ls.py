@@ -1,0 +1,83 @@
+"""The generic sparse least-squares solver (cpp_ls.cg_least_squares -> C ABI -> CUDA) against
+the oracle and the reference's golden vectors.  Bit-exact: the CUDA path reproduces the
+reference's floating-point association order at the selected thread_count."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal, load_golden
+from movie_recommender_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["ls_200x50", "ls_sparse"])
+def test_ls_matches_reference_golden_bitexact(require_gpu, cpp_ls, name):
+    g = load_golden(name)
+    for T in (1, 4):
+        cpp_ls.set_thread_count(T)
+        for alg in (1, 2):
+            x, it, rr = cpp_ls.cg_least_squares(g["rowptr"], g["colidx"], g["vals"], int(g["cols"]),
+                                                g["b"], algorithm=alg, x0=g["x0"])
+            assert x.shape == (int(g["cols"]), 1)
+            assert it == int(g["it_T%d_a%d" % (T, alg)])
+            assert bits_equal(x, g["x_T%d_a%d" % (T, alg)])
+            assert bits_equal([rr], [g["rr_T%d_a%d" % (T, alg)]])
+
+
+@pytest.mark.parametrize("T", [1, 3, 8, 64])
+@pytest.mark.parametrize("alg", [1, 2])
+def test_ls_random_sparse_bitexact_vs_oracle(require_gpu, cpp_ls, oracle, T, alg):
+    rowptr, col, vals, cols, b, x0, x_real = synth.random_sparse_system(20000, 500, 9, seed=T)
+    cpp_ls.set_thread_count(T)
+    x, it, rr = cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, algorithm=alg, x0=x0)
+    xo, ito, rro = oracle.cg_least_squares(rowptr, col, vals, cols, b, x0, algorithm=alg,
+                                           thread_count=T)
+    assert it == ito and bits_equal(x, xo) and bits_equal([rr], [rro])
+    # the reference's own acceptance criterion (cpp/ls/main.cpp:356-464): planted x recovered
+    assert np.sum(np.abs(x.reshape(-1) - x_real)) <= 0.01 * cols * 5
+
+
+def test_ls_termination_rules_bitexact(require_gpu, cpp_ls, oracle):
+    rowptr, col, vals, cols, b, x0, _ = synth.random_sparse_system(4000, 200, 5, seed=77)
+    cpp_ls.set_thread_count(4)
+    for mrd, maxit in [(0.01, 200), (0.01, 3), (0.5, 200), (-1e300, 40), (0.01, 0)]:
+        x, it, rr = cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, mrd, maxit, x0=x0)
+        xo, ito, rro = oracle.cg_least_squares(rowptr, col, vals, cols, b, x0, mrd, maxit,
+                                               thread_count=4)
+        assert it == ito and bits_equal(x, xo) and bits_equal([rr], [rro]), (mrd, maxit)
+
+
+def test_ls_ragged_rows_and_empty_columns(require_gpu, cpp_ls, oracle):
+    rng = np.random.default_rng(8)
+    rows, cols = 3000, 90
+    deg = rng.integers(0, 12, size=rows)
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    col = rng.integers(0, cols - 10, size=int(rowptr[-1])).astype(np.int32)  # last 10 cols empty
+    vals = rng.standard_normal(len(col))
+    b = rng.standard_normal(rows)
+    x0 = rng.uniform(-1, 1, cols)
+    cpp_ls.set_thread_count(5)
+    for alg in (1, 2):
+        x, it, rr = cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, algorithm=alg, x0=x0)
+        xo, ito, rro = oracle.cg_least_squares(rowptr, col, vals, cols, b, x0, algorithm=alg,
+                                               thread_count=5)
+        assert it == ito and bits_equal(x, xo) and bits_equal([rr], [rro])
+        assert bits_equal(x.reshape(-1)[-10:], x0[-10:])  # untouched unknowns keep x0
+
+
+def test_bias_model_bitexact_and_solves(require_gpu, cpp_ls, oracle):
+    """Config 2's model at a size the oracle finishes in seconds."""
+    nu, ni, nnz = 3000, 1200, 200000
+    u, i = synth.rating_pairs(nu, ni, nnz, 3, 3, seed=21)
+    raw = synth.planted_ratings(u, i, nu, ni, seed=21, subtract_median=False)
+    rowptr, col, vals, cols, b, x0 = synth.bias_model_system(u, i, raw, nu, ni, seed=21)
+    cpp_ls.set_thread_count(8)
+    x, it, rr = cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, x0=x0)
+    xo, ito, rro = oracle.cg_least_squares(rowptr, col, vals, cols, b, x0, thread_count=8)
+    assert it == ito and bits_equal(x, xo) and rr < 1e-6
+
+
+def test_dimension_mismatch_is_an_error_not_a_crash(require_gpu, cpp_ls):
+    rowptr, col, vals, cols, b, x0, _ = synth.random_sparse_system(100, 20, 3, seed=1)
+    with pytest.raises(cpp_ls.CppLsError):
+        cpp_ls.cg_least_squares(rowptr, col, vals, cols, b[:-1], x0=x0)
