@@ -1,12 +1,487 @@
-// Gram-block ALS modes (algorithm 3 and 4) -- see als.cuh.
+// Gram-block ALS (algorithm 4: gathered Gram + in-shared-memory Cholesky; algorithm 3: the
+// reference's global-scalar CG run on the stored Gram blocks).  See als.cuh for the data layout.
+//
+// K1 "gather-Gram".  Every row r of the reference's materialised user_A touches only user u's
+// k+1 columns (matrix.cpp:923-934), so A^T A is block diagonal with
+//     G_u = sum_{i in I_u} a_i a_i^T,   a_i = [item_factors[i, 0..k-1], 1]        (user side)
+//     G_i = sum_{u in U_i} a_u a_u^T,   a_u =  user_factors[u, 0..k-1]            (item side)
+// and A^T b = concat(g_o), g_o = sum b a  with b = rating (user side) or rating - user bias
+// (item side, matrix.cpp:1012-1031).  One warp walks an owner's ratings (CSR for users, CSC for
+// items, both precomputed by K4), gathers the opposite side's factor rows straight from L2/HBM
+// into mma fragments and accumulates the AUGMENTED Gram matrix  sum [a;b][a;b]^T  in fp64 on the
+// tensor cores (mma.sync m8n8k4 f64, SASS DMMA.8x8x4; measured 37.1 TFLOP/s on this B200,
+// vs 33.8 for DFMA -- tools/fp64_peak.cu).  Only the lower-triangular 8x8 tiles are computed.
+// The fragment for 8-wide tile t of ratings q..q+3 is the same register whether it is used as
+// the A operand (row.k) or the B operand (k.col), so one set of loads feeds both.
+//
+// K2b "Cholesky".  The augmented matrix is staged in shared memory; its Cholesky factor's last
+// row is y = L^-1 g, so forward substitution is free and only L^T x = y remains.  lambda = 0 as
+// in the reference: unknowns the data do not determine (pivot <= 1e-12 of the original
+// diagonal) keep their previous value (the solve is for the correction to the warm start).
+//
+// Heavy owners are cut into segments of SEG ratings processed by different warps; the partial
+// Gram matrices are summed in SEGMENT ORDER by whichever warp finishes last, so the result does
+// not depend on scheduling (deterministic, no floating-point atomics).
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
 #include "als.cuh"
 
 namespace mrb {
 
-struct AlsProblem::GramState {};
+namespace {
 
-AlsRunInfo AlsProblem::run_gram(int, double, int) {
-    throw Error(kErrArgument, "als: algorithm 3/4 not built yet");
+constexpr int GRAM_SEG = 2048;     // ratings per work item
+constexpr int GRAM_WARPS = 4;      // warps per CTA
+
+struct WorkItem {
+    int owner;   // row of the factor matrix being solved
+    int beg;     // first grouped rating position
+    int end;     // one past the last
+    int seg;     // segment index within the owner
+    int nseg;    // number of segments of the owner
+    int slot;    // multi-segment owners: index of the owner's first partial buffer / counter id
+    int multi;   // multi-segment owners: dense id (counter index), else -1
+    int pad;
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Leading dimension of the shared-memory matrix: >= m and == 4 (mod 16) so that the 8x4 lane
+// grid of the trailing update (row stride LD, 16 lanes per 64-bit phase) hits 16 distinct banks.
+__host__ __device__ constexpr int gram_ld(int m) {
+    int ld = m;
+    while (ld % 16 != 4) ld++;
+    return ld;
+}
+
+// element j of the augmented row [a; b]
+template <bool USER>
+__device__ __forceinline__ double aug_elem(const double* __restrict__ row, double rating, int j,
+                                           int k) {
+    if (j < k) return row[j];
+    if (USER) return j == k ? 1.0 : (j == k + 1 ? rating : 0.0);
+    return j == k ? rating - row[k] : 0.0;
+}
+
+struct GramArgs {
+    const WorkItem* work;
+    int n_work;
+    int* work_counter;        // dynamic scheduler
+    const int* other_g;       // opposite-side id of each grouped rating position
+    const double* rating_g;   // rating of each grouped rating position
+    const double* other_f;    // opposite-side factors
+    int other_stride;
+    int k;                    // gathered factor count
+    int n;                    // unknowns per owner (k+1 users, k items)
+    double* x;                // owner factors, in/out, row stride n
+    double* partials;         // [slot][ST*64] partial augmented Gram tiles (multi-segment owners)
+    int* seg_done;            // [multi] arrival counters
+    double* G_out;            // EPI_STORE: [owner][n*n]
+    double* g_out;            // EPI_STORE: [owner][n]
+    double* sse_out;          // optional [owner]: sum of squared residuals after the solve
+};
+
+enum { EPI_SOLVE = 0, EPI_STORE = 1 };
+
+template <int M8, bool USER, int EPI>
+__global__ void __launch_bounds__(GRAM_WARPS * 32)
+k_gram(const GramArgs A) {
+    constexpr int ST = M8 * (M8 + 1) / 2;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane & 3, p = lane >> 2;
+    const int n = A.n, m = n + 1, k = A.k;
+    const int LD = gram_ld(m);
+    const int per_warp = m * LD + 2 * n;
+    double* S = smem + static_cast<size_t>(warp) * per_warp;   // (n+1) x LD
+    double* x0s = S + m * LD;                                   // n
+    double* d0 = x0s + n;                                       // n
+
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(A.work_counter, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= A.n_work) break;
+        const WorkItem wi = A.work[w];
+
+        // ---------------- K1: accumulate the augmented Gram tiles ----------------
+        double acc[ST][2];
+#pragma unroll
+        for (int t = 0; t < ST; t++) { acc[t][0] = 0; acc[t][1] = 0; }
+
+        const int cnt = wi.end - wi.beg;
+        const int nsteps = (cnt + 3) >> 2;
+        int ids_cur = 0, ids_nxt = 0;
+        double rts_cur = 0, rts_nxt = 0;
+        if (lane < cnt) { ids_cur = A.other_g[wi.beg + lane]; rts_cur = A.rating_g[wi.beg + lane]; }
+        if (32 + lane < cnt) { ids_nxt = A.other_g[wi.beg + 32 + lane]; rts_nxt = A.rating_g[wi.beg + 32 + lane]; }
+        double f_next[M8];
+        {
+            const int id = __shfl_sync(0xffffffffu, ids_cur, q);
+            const double rt = shfl_double(rts_cur, q);
+            const bool valid = q < cnt;
+            const double* row = A.other_f + static_cast<size_t>(id) * A.other_stride;
+#pragma unroll
+            for (int t = 0; t < M8; t++) f_next[t] = valid ? aug_elem<USER>(row, rt, t * 8 + p, k) : 0.0;
+        }
+        for (int step = 0; step < nsteps; step++) {
+            double f[M8];
+#pragma unroll
+            for (int t = 0; t < M8; t++) f[t] = f_next[t];
+            const int ns = step + 1;
+            if (ns < nsteps) {
+                if ((ns & 7) == 0) {
+                    ids_cur = ids_nxt;
+                    rts_cur = rts_nxt;
+                    const int e = (ns << 2) + 32 + lane;
+                    ids_nxt = 0;
+                    rts_nxt = 0;
+                    if (e < cnt) { ids_nxt = A.other_g[wi.beg + e]; rts_nxt = A.rating_g[wi.beg + e]; }
+                }
+                const int src = ((ns & 7) << 2) + q;
+                const int id = __shfl_sync(0xffffffffu, ids_cur, src);
+                const double rt = shfl_double(rts_cur, src);
+                const bool valid = (ns << 2) + q < cnt;
+                const double* row = A.other_f + static_cast<size_t>(id) * A.other_stride;
+#pragma unroll
+                for (int t = 0; t < M8; t++) f_next[t] = valid ? aug_elem<USER>(row, rt, t * 8 + p, k) : 0.0;
+            }
+            int idx = 0;
+#pragma unroll
+            for (int ti = 0; ti < M8; ti++)
+#pragma unroll
+                for (int tj = 0; tj <= ti; tj++) {
+                    dmma884(acc[idx][0], acc[idx][1], f[ti], f[tj]);
+                    idx++;
+                }
+        }
+
+        // ---------------- multi-segment owners: ordered reduction by the last arriver --------
+        if (wi.nseg > 1) {
+            double* mine = A.partials + (static_cast<size_t>(wi.slot) + wi.seg) * (ST * 64);
+#pragma unroll
+            for (int t = 0; t < ST; t++)
+                *reinterpret_cast<double2*>(mine + (t * 32 + lane) * 2) = make_double2(acc[t][0], acc[t][1]);
+            __threadfence();
+            __syncwarp();
+            int arrived = 0;
+            if (lane == 0) arrived = atomicAdd(A.seg_done + wi.multi, 1);
+            arrived = __shfl_sync(0xffffffffu, arrived, 0);
+            if (arrived != wi.nseg - 1) continue;   // someone else finishes this owner
+            __threadfence();
+#pragma unroll
+            for (int t = 0; t < ST; t++) { acc[t][0] = 0; acc[t][1] = 0; }
+            for (int s = 0; s < wi.nseg; s++) {
+                const double* src = A.partials + (static_cast<size_t>(wi.slot) + s) * (ST * 64);
+#pragma unroll
+                for (int t = 0; t < ST; t++) {
+                    const double2 v = __ldcg(reinterpret_cast<const double2*>(src + (t * 32 + lane) * 2));
+                    acc[t][0] += v.x;
+                    acc[t][1] += v.y;
+                }
+            }
+        }
+
+        // ---------------- stage [G g; g^T s] in shared memory (both triangles of G) ----------
+        {
+            int idx = 0;
+#pragma unroll
+            for (int ti = 0; ti < M8; ti++)
+#pragma unroll
+                for (int tj = 0; tj <= ti; tj++) {
+                    const int i = ti * 8 + p;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int j = tj * 8 + 2 * q + h;
+                        if (i <= n && j <= n) {
+                            S[i * LD + j] = acc[idx][h];
+                            if (ti != tj) S[j * LD + i] = acc[idx][h];
+                        }
+                    }
+                    idx++;
+                }
+        }
+        __syncwarp();
+        double* xo = A.x + static_cast<size_t>(wi.owner) * n;
+
+        if (EPI == EPI_STORE) {
+            double* Go = A.G_out + static_cast<size_t>(wi.owner) * n * n;
+            for (int e = lane; e < n * n; e += 32) Go[e] = S[(e / n) * LD + (e % n)];
+            for (int c = lane; c < n; c += 32) A.g_out[static_cast<size_t>(wi.owner) * n + c] = S[n * LD + c];
+            __syncwarp();
+            continue;
+        }
+
+        // ---------------- K2b: correction-form normal equations + Cholesky -------------------
+        for (int c = lane; c < n; c += 32) { x0s[c] = xo[c]; d0[c] = S[c * LD + c]; }
+        __syncwarp();
+        // rhs' = g - G x0  (row n), column walk => conflict-free
+        for (int c = lane; c < n; c += 32) {
+            double s = S[n * LD + c];
+            for (int i = 0; i < n; i++) s -= S[i * LD + c] * x0s[i];
+            S[n * LD + c] = s;
+        }
+        __syncwarp();
+        const int li = lane >> 2, lc = lane & 3;
+        for (int j = 0; j < n; j++) {
+            const double d = S[j * LD + j];
+            const bool ok = d > 1e-12 * d0[j] && d0[j] > 0.0;   // also false for NaN
+            if (ok) {
+                const double inv = 1.0 / sqrt(d);
+                for (int i = j + 1 + lane; i <= n; i += 32) S[i * LD + j] *= inv;
+                __syncwarp();
+                if (lane == 0) S[j * LD + j] = d * inv;
+                for (int i0 = j + 1; i0 <= n; i0 += 8) {
+                    const int i = i0 + li;
+                    const double Lij = i <= n ? S[i * LD + j] : 0.0;
+                    const int cmax = min(i0 + 7, n - 1);
+                    for (int c0 = j + 1; c0 <= cmax; c0 += 4) {
+                        const int c = c0 + lc;
+                        if (i <= n && c <= i && c < n) S[i * LD + c] -= Lij * S[c * LD + j];
+                    }
+                }
+            } else {
+                // undetermined unknown: no correction, no coupling
+                for (int i = j + 1 + lane; i <= n; i += 32) S[i * LD + j] = 0.0;
+                if (lane == 0) S[j * LD + j] = 0.0;
+            }
+            __syncwarp();
+        }
+        // back substitution  L^T delta = y  (y = row n), column oriented
+        double delta[(M8 * 8 + 31) / 32];
+#pragma unroll
+        for (int s = 0; s < (M8 * 8 + 31) / 32; s++) delta[s] = 0;
+        for (int j = n - 1; j >= 0; j--) {
+            const double Ljj = S[j * LD + j];
+            const double dj = Ljj != 0.0 ? S[n * LD + j] / Ljj : 0.0;
+#pragma unroll
+            for (int s = 0; s < (M8 * 8 + 31) / 32; s++)
+                if (lane + 32 * s == j) delta[s] = dj;
+            for (int c = lane; c < j; c += 32) S[n * LD + c] -= S[j * LD + c] * dj;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int s = 0; s < (M8 * 8 + 31) / 32; s++) {
+            const int c = lane + 32 * s;
+            if (c < n) xo[c] = x0s[c] + delta[s];
+        }
+        __syncwarp();
+    }
+}
+
+// Sum of squared training errors, deterministic: per-CTA partials in fixed tree order.
+__global__ void __launch_bounds__(256)
+k_sse_partials(const int* __restrict__ user_ids, const int* __restrict__ item_ids,
+               const double* __restrict__ ratings, const double* __restrict__ uf,
+               const double* __restrict__ itf, int k, int nnz, double* __restrict__ partials) {
+    __shared__ double red[256];
+    double s = 0;
+    for (long long r = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; r < nnz;
+         r += static_cast<long long>(gridDim.x) * 256) {
+        const double* u = uf + static_cast<size_t>(user_ids[r]) * (k + 1);
+        const double* v = itf + static_cast<size_t>(item_ids[r]) * k;
+        double pred = u[k];
+        for (int j = 0; j < k; j++) pred += u[j] * v[j];
+        const double d = pred - ratings[r];
+        s += d * d;
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
+}
+
+__global__ void k_gather_grouped(const int* __restrict__ idx, const int* __restrict__ other_ids,
+                                 const double* __restrict__ ratings, int nnz,
+                                 int* __restrict__ other_g, double* __restrict__ rating_g) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const int r = idx[e];
+    other_g[e] = other_ids[r];
+    rating_g[e] = ratings[r];
+}
+
+struct Side {
+    DevBuf<int> other_g;
+    DevBuf<double> rating_g;
+    DevBuf<WorkItem> work;
+    int n_work = 0;
+    int n_multi = 0;
+    int n_slots = 0;
+};
+
+void build_side(Side& sd, const int* d_ptr, const int* d_idx, const int* d_other_ids,
+                const double* d_ratings, int owners, int nnz, cudaStream_t s) {
+    sd.other_g.alloc(nnz);
+    sd.rating_g.alloc(nnz);
+    if (nnz)
+        k_gather_grouped<<<ceil_div(nnz, 256), 256, 0, s>>>(d_idx, d_other_ids, d_ratings, nnz,
+                                                            sd.other_g.p, sd.rating_g.p);
+    MRB_CUDA(cudaGetLastError());
+    std::vector<int> ptr(static_cast<size_t>(owners) + 1);
+    MRB_CUDA(cudaMemcpyAsync(ptr.data(), d_ptr, sizeof(int) * ptr.size(), cudaMemcpyDeviceToHost, s));
+    MRB_CUDA(cudaStreamSynchronize(s));
+    // longest-processing-time-first order: owners by descending degree (stable)
+    std::vector<int> order(owners);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b];
+    });
+    std::vector<WorkItem> work;
+    work.reserve(owners + nnz / GRAM_SEG + 1);
+    sd.n_multi = 0;
+    sd.n_slots = 0;
+    for (int o : order) {
+        const int beg = ptr[o], end = ptr[o + 1];
+        const int deg = end - beg;
+        if (deg == 0) continue;  // no equations: the factors keep their previous value
+        const int nseg = deg <= GRAM_SEG ? 1 : (deg + GRAM_SEG - 1) / GRAM_SEG;
+        for (int sg = 0; sg < nseg; sg++) {
+            WorkItem wi;
+            wi.owner = o;
+            wi.beg = beg + sg * GRAM_SEG;
+            wi.end = std::min(end, wi.beg + GRAM_SEG);
+            wi.seg = sg;
+            wi.nseg = nseg;
+            wi.slot = nseg > 1 ? sd.n_slots : 0;
+            wi.multi = nseg > 1 ? sd.n_multi : -1;
+            wi.pad = 0;
+            work.push_back(wi);
+        }
+        if (nseg > 1) { sd.n_multi++; sd.n_slots += nseg; }
+    }
+    sd.n_work = static_cast<int>(work.size());
+    sd.work.alloc(work.size());
+    MRB_CUDA(cudaMemcpyAsync(sd.work.p, work.data(), sizeof(WorkItem) * work.size(),
+                             cudaMemcpyHostToDevice, s));
+    MRB_CUDA(cudaStreamSynchronize(s));
+}
+
+template <int M8, bool USER, int EPI>
+void launch_gram(const GramArgs& a, int sms, cudaStream_t s) {
+    const int m = a.n + 1;
+    const size_t smem = sizeof(double) * GRAM_WARPS * (static_cast<size_t>(m) * gram_ld(m) + 2 * a.n);
+    auto kern = k_gram<M8, USER, EPI>;
+    static size_t cached_smem = 0;
+    static int per_sm = 0;
+    if (cached_smem != smem) {
+        MRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+        MRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GRAM_WARPS * 32, smem));
+        cached_smem = smem;
+    }
+    MRB_REQUIRE(per_sm >= 1, "gram kernel does not fit on an SM");
+    const int grid = std::min(sms * per_sm, ceil_div(a.n_work, GRAM_WARPS));
+    kern<<<grid > 0 ? grid : 1, GRAM_WARPS * 32, smem, s>>>(a);
+    MRB_CUDA(cudaGetLastError());
+}
+
+template <bool USER, int EPI>
+void dispatch_gram(const GramArgs& a, int sms, cudaStream_t s) {
+    const int m8 = (a.n + 1 + 7) / 8;
+    switch (m8) {
+        case 1: launch_gram<1, USER, EPI>(a, sms, s); break;
+        case 2: launch_gram<2, USER, EPI>(a, sms, s); break;
+        case 3: launch_gram<3, USER, EPI>(a, sms, s); break;
+        case 4: launch_gram<4, USER, EPI>(a, sms, s); break;
+        case 5: launch_gram<5, USER, EPI>(a, sms, s); break;
+        case 6: launch_gram<6, USER, EPI>(a, sms, s); break;
+        case 7: launch_gram<7, USER, EPI>(a, sms, s); break;
+        default:
+            throw Error(kErrArgument, "als algorithm 3/4: rank above 54 is not supported yet");
+    }
+}
+
+}  // namespace
+
+struct AlsProblem::GramState {
+    Side user, item;
+    DevBuf<double> partials;
+    DevBuf<int> counters;      // [0] work counter, [1..] segment arrival counters
+    DevBuf<double> sse_partials;
+    int sms = 148;
+    int st_doubles = 0;
+};
+
+AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_iteration) {
+    MRB_REQUIRE(algorithm == ALS_GRAM_CHOLESKY, "als: algorithm 3 not built yet");
+    const int n_u = k_ + 1, n_i = k_;
+    const int m8 = (n_u + 1 + 7) / 8;
+    MRB_REQUIRE(m8 <= 7, "als algorithm 3/4: rank above 54 is not supported yet");
+    if (!gram_) {
+        gram_ = std::make_shared<GramState>();
+        GramState& g = *gram_;
+        int dev = 0;
+        MRB_CUDA(cudaGetDevice(&dev));
+        MRB_CUDA(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, dev));
+        build_side(g.user, u_ptr_.p, u_idx_.p, item_ids_.p, ratings_.p, nu_, nnz_, s_);
+        build_side(g.item, i_ptr_.p, i_idx_.p, user_ids_.p, ratings_.p, ni_, nnz_, s_);
+        g.st_doubles = m8 * (m8 + 1) / 2 * 64;
+        const int slots = std::max(g.user.n_slots, g.item.n_slots);
+        g.partials.alloc(static_cast<size_t>(std::max(slots, 1)) * g.st_doubles);
+        g.counters.alloc(1 + static_cast<size_t>(std::max(std::max(g.user.n_multi, g.item.n_multi), 1)));
+        g.sse_partials.alloc(1024);
+    }
+    GramState& g = *gram_;
+    std::vector<double> h_sse(1024);
+
+    auto half = [&](bool user_side) {
+        Side& sd = user_side ? g.user : g.item;
+        MRB_CUDA(cudaMemsetAsync(g.counters.p, 0, sizeof(int) * g.counters.n, s_));
+        GramArgs a{};
+        a.work = sd.work.p;
+        a.n_work = sd.n_work;
+        a.work_counter = g.counters.p;
+        a.other_g = sd.other_g.p;
+        a.rating_g = sd.rating_g.p;
+        a.other_f = user_side ? itf_.p : uf_.p;
+        a.other_stride = user_side ? k_ : k_ + 1;
+        a.k = k_;
+        a.n = user_side ? n_u : n_i;
+        a.x = user_side ? uf_.p : itf_.p;
+        a.partials = g.partials.p;
+        a.seg_done = g.counters.p + 1;
+        if (sd.n_work == 0) return;
+        if (user_side) dispatch_gram<true, EPI_SOLVE>(a, g.sms, s_);
+        else dispatch_gram<false, EPI_SOLVE>(a, g.sms, s_);
+    };
+
+    AlsRunInfo info;
+    int sweep = 0;
+    double old_rr = 0;
+    while (sweep < max_iteration) {
+        half(true);
+        half(false);
+        // rr := sum of squared training errors (the exact solve leaves no normal-equation
+        // residual to monitor); same relative-decrease rule as matrix.cpp:871-875.
+        k_sse_partials<<<1024, 256, 0, s_>>>(user_ids_.p, item_ids_.p, ratings_.p, uf_.p, itf_.p, k_,
+                                             nnz_, g.sse_partials.p);
+        MRB_CUDA(cudaGetLastError());
+        MRB_CUDA(cudaMemcpyAsync(h_sse.data(), g.sse_partials.p, sizeof(double) * 1024,
+                                 cudaMemcpyDeviceToHost, s_));
+        MRB_CUDA(cudaStreamSynchronize(s_));
+        double rr = 0;
+        for (double v : h_sse) rr += v;
+        info.sweeps_run++;
+        info.last_rr = rr;
+        if (sweep >= 3) {
+            const double decrease = (old_rr - rr) / old_rr;
+            if (decrease < min_r_decrease) break;
+        }
+        old_rr = rr;
+        sweep++;
+    }
+    info.sweeps_returned = sweep;
+    return info;
 }
 
 }  // namespace mrb
