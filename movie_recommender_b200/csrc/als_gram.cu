@@ -52,14 +52,6 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// Leading dimension of the shared-memory matrix: >= m and == 4 (mod 16) so that the 8x4 lane
-// grid of the trailing update (row stride LD, 16 lanes per 64-bit phase) hits 16 distinct banks.
-__host__ __device__ constexpr int gram_ld(int m) {
-    int ld = m;
-    while (ld % 16 != 4) ld++;
-    return ld;
-}
-
 // element j of the augmented row [a; b]
 template <bool USER>
 __device__ __forceinline__ double aug_elem(const double* __restrict__ row, double rating, int j,
@@ -89,19 +81,225 @@ struct GramArgs {
 
 enum { EPI_SOLVE = 0, EPI_STORE = 1 };
 
+// index of lower-triangular tile (ti, tj), tj <= ti
+__host__ __device__ constexpr int TI(int ti, int tj) { return ti * (ti + 1) / 2 + tj; }
+
+__device__ __forceinline__ double xor_sum_p(double v) {   // sum over the 8 lanes sharing q
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
+__device__ __forceinline__ double xor_sum_q(double v) {   // sum over the 4 lanes sharing p
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2b: register-resident blocked Cholesky on the mma accumulator fragments.
+//
+// The augmented matrix [G g; g^T s] (order n+1 <= 8*M8) sits in the lower-triangular 8x8 tiles
+// acc[TI(ti,tj)]; lane (p = lane>>2, q = lane&3) holds elements (row p, cols 2q, 2q+1) of every
+// tile.  Right-looking by tile column tk:
+//   1. the 8 pivot columns of tile column tk are eliminated one by one with warp shuffles
+//      (diagonal tile and the panel tiles below it together);
+//   2. the trailing tiles get  T(ti,tj) -= L(ti,tk) L(tj,tk)^T  on the tensor cores (2 DMMA per
+//      tile; the C-fragment -> A/B-fragment conversion is two shuffles per 8x4 chunk).
+// Row n of the factor is y = L^-1 g', so only the back substitution L^T delta = y remains; it is
+// done on the fragments as well.  No shared memory is used.
+// The system solved is the CORRECTION form  G delta = g - G x0,  x = x0 + delta: unknowns whose
+// pivot falls below 1e-12 of the original diagonal get delta = 0 (they keep their previous value,
+// as they do under the reference's warm-started CG), the others are solved consistently.
+// ------------------------------------------------------------------------------------------
+template <int M8>
+__device__ __forceinline__ void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], int n,
+                                           double* __restrict__ xo, double* __restrict__ sse_slot,
+                                           int lane) {
+    constexpr int TN = M8 - 1;            // tile row/column holding index n (the rhs)
+    const int p = lane >> 2, q = lane & 3;
+    const int pr = n & 7;
+
+    // ---- x0 in row-indexed (xp) and column-indexed (xq) layouts; zero beyond n
+    double xp[M8], xq[M8][2];
+#pragma unroll
+    for (int t = 0; t < M8; t++) {
+        const int r = 8 * t + p;
+        xp[t] = r < n ? xo[r] : 0.0;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int c = 8 * t + 2 * q + s;
+            xq[t][s] = c < n ? xo[c] : 0.0;
+        }
+    }
+    // ---- v = G x0 in column layout (replicated over p)
+    double vy[M8][2];
+    {
+        double colsum[M8][2], rowsum[M8];
+#pragma unroll
+        for (int t = 0; t < M8; t++) { colsum[t][0] = 0; colsum[t][1] = 0; rowsum[t] = 0; }
+#pragma unroll
+        for (int ti = 0; ti < M8; ti++)
+#pragma unroll
+            for (int tj = 0; tj <= ti; tj++) {
+                colsum[tj][0] += acc[TI(ti, tj)][0] * xp[ti];
+                colsum[tj][1] += acc[TI(ti, tj)][1] * xp[ti];
+                if (ti != tj) rowsum[ti] += acc[TI(ti, tj)][0] * xq[tj][0] + acc[TI(ti, tj)][1] * xq[tj][1];
+            }
+#pragma unroll
+        for (int t = 0; t < M8; t++) {
+            colsum[t][0] = xor_sum_p(colsum[t][0]);
+            colsum[t][1] = xor_sum_p(colsum[t][1]);
+            rowsum[t] = xor_sum_q(rowsum[t]);   // indexed by p, replicated over q
+        }
+#pragma unroll
+        for (int t = 0; t < M8; t++)
+#pragma unroll
+            for (int s = 0; s < 2; s++)
+                vy[t][s] = colsum[t][s] + shfl_double(rowsum[t], (2 * q + s) * 4);
+    }
+    // ---- rhs' = g - G x0 on the augmented row; x0.(g + g') for the residual bookkeeping
+    double gdot = 0;
+#pragma unroll
+    for (int t = 0; t < M8; t++)
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int c = 8 * t + 2 * q + s;
+            if (p == pr && c < n) {
+                const double g0 = acc[TI(TN, t)][s];
+                const double g1 = g0 - vy[t][s];
+                acc[TI(TN, t)][s] = g1;
+                gdot += xq[t][s] * (g0 + g1);
+            }
+        }
+    gdot = xor_sum_q(gdot);   // valid on lanes with p == pr
+
+    // ---- pivot thresholds from the original diagonal: lane (p, p>>1) holds column 8t+p's
+    double thr[M8];
+#pragma unroll
+    for (int t = 0; t < M8; t++) thr[t] = 1e-12 * ((p & 1) ? acc[TI(t, t)][1] : acc[TI(t, t)][0]);
+
+    double invd[M8];   // lane (p, *) : 1/L[j][j] for j = 8t+p (0 for a skipped pivot)
+#pragma unroll
+    for (int t = 0; t < M8; t++) invd[t] = 0;
+
+#pragma unroll
+    for (int tk = 0; tk < M8; tk++) {
+        const int D = TI(tk, tk);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            if (8 * tk + c < n) {   // warp-uniform: only the last tile column has non-pivot columns
+                const int src_cc = c * 4 + (c >> 1);
+                const double d = shfl_double(acc[D][c & 1], src_cc);
+                const double th = shfl_double(thr[tk], src_cc);
+                const bool ok = d > th && th > 0.0;   // false for NaN
+                const double inv = ok ? rsqrt(d) : 0.0;
+                if (p == c) invd[tk] = inv;
+                if (q == (c >> 1)) {
+                    const double v = acc[D][c & 1];
+                    if (p >= c) acc[D][c & 1] = ok ? v * inv : 0.0;   // p == c: d * rsqrt(d) = sqrt(d)
+#pragma unroll
+                    for (int ti = tk + 1; ti < M8; ti++)
+                        acc[TI(ti, tk)][c & 1] = ok ? acc[TI(ti, tk)][c & 1] * inv : 0.0;
+                }
+                if (c < 7) {
+                    // D[c2][c] for this lane's two columns c2 = 2q, 2q+1
+                    const double dc20 = shfl_double(acc[D][c & 1], (2 * q) * 4 + (c >> 1));
+                    const double dc21 = shfl_double(acc[D][c & 1], (2 * q + 1) * 4 + (c >> 1));
+#pragma unroll
+                    for (int ti = tk; ti < M8; ti++) {
+                        const int X = TI(ti, tk);
+                        const double xrc = shfl_double(acc[X][c & 1], p * 4 + (c >> 1));   // X[p][c]
+                        if (2 * q > c) acc[X][0] -= xrc * dc20;
+                        if (2 * q + 1 > c) acc[X][1] -= xrc * dc21;
+                    }
+                }
+            }
+        }
+        if (tk < M8 - 1) {
+            // trailing update on the tensor cores
+            double ax[M8][2];
+#pragma unroll
+            for (int ti = tk + 1; ti < M8; ti++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int src = p * 4 + 2 * h + (q >> 1);
+                    const double v0 = shfl_double(acc[TI(ti, tk)][0], src);
+                    const double v1 = shfl_double(acc[TI(ti, tk)][1], src);
+                    ax[ti][h] = (q & 1) ? v1 : v0;   // L(ti,tk)[p][4h+q]
+                }
+#pragma unroll
+            for (int ti = tk + 1; ti < M8; ti++)
+#pragma unroll
+                for (int tj = tk + 1; tj <= ti; tj++) {
+                    dmma884(acc[TI(ti, tj)][0], acc[TI(ti, tj)][1], -ax[ti][0], ax[tj][0]);
+                    dmma884(acc[TI(ti, tj)][0], acc[TI(ti, tj)][1], -ax[ti][1], ax[tj][1]);
+                }
+        }
+    }
+
+    // ---- residual: corner - x0.(g + g')  ==  sum (b - a.x)^2 at the solution
+    if (sse_slot != nullptr) {
+        const double corner = (pr & 1) ? acc[TI(TN, TN)][1] : acc[TI(TN, TN)][0];
+        if (p == pr && q == (pr >> 1)) *sse_slot = corner - gdot;
+    }
+
+    // ---- back substitution L^T delta = y
+    double y[M8][2], dl[M8][2];
+#pragma unroll
+    for (int t = 0; t < M8; t++)
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            y[t][s] = shfl_double(acc[TI(TN, t)][s], pr * 4 + q);
+            dl[t][s] = 0;
+        }
+#pragma unroll
+    for (int tj = M8 - 1; tj >= 0; tj--) {
+        const int D = TI(tj, tj);
+#pragma unroll
+        for (int c = 7; c >= 0; c--) {
+            if (8 * tj + c < n) {
+                const double yc = shfl_double(y[tj][c & 1], c >> 1);
+                const double inv = shfl_double(invd[tj], c * 4);
+                const double dc = yc * inv;
+                if (q == (c >> 1)) dl[tj][c & 1] = dc;
+                if (c > 0) {
+                    const double l0 = shfl_double(acc[D][0], c * 4 + q);   // L[c][2q]
+                    const double l1 = shfl_double(acc[D][1], c * 4 + q);   // L[c][2q+1]
+                    if (2 * q < c) y[tj][0] -= l0 * dc;
+                    if (2 * q + 1 < c) y[tj][1] -= l1 * dc;
+                }
+            }
+        }
+        if (tj > 0) {
+            const double v0 = shfl_double(dl[tj][0], p >> 1);
+            const double v1 = shfl_double(dl[tj][1], p >> 1);
+            const double dp = (p & 1) ? v1 : v0;   // delta[8 tj + p] (0 for rows >= n)
+#pragma unroll
+            for (int t2 = 0; t2 < tj; t2++) {
+                y[t2][0] -= xor_sum_p(acc[TI(tj, t2)][0] * dp);
+                y[t2][1] -= xor_sum_p(acc[TI(tj, t2)][1] * dp);
+            }
+        }
+    }
+    if (p == 0) {
+#pragma unroll
+        for (int t = 0; t < M8; t++)
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const int c = 8 * t + 2 * q + s;
+                if (c < n) xo[c] = xq[t][s] + dl[t][s];
+            }
+    }
+}
+
 template <int M8, bool USER, int EPI>
 __global__ void __launch_bounds__(GRAM_WARPS * 32)
 k_gram(const GramArgs A) {
     constexpr int ST = M8 * (M8 + 1) / 2;
-    extern __shared__ double smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int q = lane & 3, p = lane >> 2;
-    const int n = A.n, m = n + 1, k = A.k;
-    const int LD = gram_ld(m);
-    const int per_warp = m * LD + 2 * n;
-    double* S = smem + static_cast<size_t>(warp) * per_warp;   // (n+1) x LD
-    double* x0s = S + m * LD;                                   // n
-    double* d0 = x0s + n;                                       // n
+    const int n = A.n, k = A.k;
 
     for (;;) {
         int w = 0;
@@ -152,14 +350,11 @@ k_gram(const GramArgs A) {
 #pragma unroll
                 for (int t = 0; t < M8; t++) f_next[t] = valid ? aug_elem<USER>(row, rt, t * 8 + p, k) : 0.0;
             }
-            int idx = 0;
 #pragma unroll
             for (int ti = 0; ti < M8; ti++)
 #pragma unroll
-                for (int tj = 0; tj <= ti; tj++) {
-                    dmma884(acc[idx][0], acc[idx][1], f[ti], f[tj]);
-                    idx++;
-                }
+                for (int tj = 0; tj <= ti; tj++)
+                    dmma884(acc[TI(ti, tj)][0], acc[TI(ti, tj)][1], f[ti], f[tj]);
         }
 
         // ---------------- multi-segment owners: ordered reduction by the last arriver --------
@@ -188,90 +383,28 @@ k_gram(const GramArgs A) {
             }
         }
 
-        // ---------------- stage [G g; g^T s] in shared memory (both triangles of G) ----------
-        {
-            int idx = 0;
+        if (EPI == EPI_STORE) {
+            // algorithm 3: G (row-major n x n, both triangles) and g to HBM
+            double* Go = A.G_out + static_cast<size_t>(wi.owner) * n * n;
+            double* go = A.g_out + static_cast<size_t>(wi.owner) * n;
 #pragma unroll
             for (int ti = 0; ti < M8; ti++)
 #pragma unroll
-                for (int tj = 0; tj <= ti; tj++) {
-                    const int i = ti * 8 + p;
+                for (int tj = 0; tj <= ti; tj++)
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
-                        const int j = tj * 8 + 2 * q + h;
-                        if (i <= n && j <= n) {
-                            S[i * LD + j] = acc[idx][h];
-                            if (ti != tj) S[j * LD + i] = acc[idx][h];
+                        const int i = ti * 8 + p, j = tj * 8 + 2 * q + h;
+                        const double v = acc[TI(ti, tj)][h];
+                        if (i < n && j < n) {
+                            Go[i * n + j] = v;
+                            if (ti != tj) Go[j * n + i] = v;
                         }
+                        if (i == n && j < n) go[j] = v;
                     }
-                    idx++;
-                }
-        }
-        __syncwarp();
-        double* xo = A.x + static_cast<size_t>(wi.owner) * n;
-
-        if (EPI == EPI_STORE) {
-            double* Go = A.G_out + static_cast<size_t>(wi.owner) * n * n;
-            for (int e = lane; e < n * n; e += 32) Go[e] = S[(e / n) * LD + (e % n)];
-            for (int c = lane; c < n; c += 32) A.g_out[static_cast<size_t>(wi.owner) * n + c] = S[n * LD + c];
-            __syncwarp();
             continue;
         }
-
-        // ---------------- K2b: correction-form normal equations + Cholesky -------------------
-        for (int c = lane; c < n; c += 32) { x0s[c] = xo[c]; d0[c] = S[c * LD + c]; }
-        __syncwarp();
-        // rhs' = g - G x0  (row n), column walk => conflict-free
-        for (int c = lane; c < n; c += 32) {
-            double s = S[n * LD + c];
-            for (int i = 0; i < n; i++) s -= S[i * LD + c] * x0s[i];
-            S[n * LD + c] = s;
-        }
-        __syncwarp();
-        const int li = lane >> 2, lc = lane & 3;
-        for (int j = 0; j < n; j++) {
-            const double d = S[j * LD + j];
-            const bool ok = d > 1e-12 * d0[j] && d0[j] > 0.0;   // also false for NaN
-            if (ok) {
-                const double inv = 1.0 / sqrt(d);
-                for (int i = j + 1 + lane; i <= n; i += 32) S[i * LD + j] *= inv;
-                __syncwarp();
-                if (lane == 0) S[j * LD + j] = d * inv;
-                for (int i0 = j + 1; i0 <= n; i0 += 8) {
-                    const int i = i0 + li;
-                    const double Lij = i <= n ? S[i * LD + j] : 0.0;
-                    const int cmax = min(i0 + 7, n - 1);
-                    for (int c0 = j + 1; c0 <= cmax; c0 += 4) {
-                        const int c = c0 + lc;
-                        if (i <= n && c <= i && c < n) S[i * LD + c] -= Lij * S[c * LD + j];
-                    }
-                }
-            } else {
-                // undetermined unknown: no correction, no coupling
-                for (int i = j + 1 + lane; i <= n; i += 32) S[i * LD + j] = 0.0;
-                if (lane == 0) S[j * LD + j] = 0.0;
-            }
-            __syncwarp();
-        }
-        // back substitution  L^T delta = y  (y = row n), column oriented
-        double delta[(M8 * 8 + 31) / 32];
-#pragma unroll
-        for (int s = 0; s < (M8 * 8 + 31) / 32; s++) delta[s] = 0;
-        for (int j = n - 1; j >= 0; j--) {
-            const double Ljj = S[j * LD + j];
-            const double dj = Ljj != 0.0 ? S[n * LD + j] / Ljj : 0.0;
-#pragma unroll
-            for (int s = 0; s < (M8 * 8 + 31) / 32; s++)
-                if (lane + 32 * s == j) delta[s] = dj;
-            for (int c = lane; c < j; c += 32) S[n * LD + c] -= S[j * LD + c] * dj;
-            __syncwarp();
-        }
-#pragma unroll
-        for (int s = 0; s < (M8 * 8 + 31) / 32; s++) {
-            const int c = lane + 32 * s;
-            if (c < n) xo[c] = x0s[c] + delta[s];
-        }
-        __syncwarp();
+        gram_solve<M8>(acc, n, A.x + static_cast<size_t>(wi.owner) * n,
+                       A.sse_out ? A.sse_out + wi.owner : nullptr, lane);
     }
 }
 
@@ -298,6 +431,21 @@ k_sse_partials(const int* __restrict__ user_ids, const int* __restrict__ item_id
         __syncthreads();
     }
     if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
+}
+
+// Fixed-order sum of n doubles (one CTA): thread t adds elements t, t+1024, ... then a tree.
+__global__ void __launch_bounds__(1024)
+k_sum_fixed(const double* __restrict__ in, int n, double* __restrict__ out) {
+    __shared__ double red[1024];
+    double s = 0;
+    for (int i = threadIdx.x; i < n; i += 1024) s += in[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 512; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
 }
 
 __global__ void k_gather_grouped(const int* __restrict__ idx, const int* __restrict__ other_ids,
@@ -368,20 +516,14 @@ void build_side(Side& sd, const int* d_ptr, const int* d_idx, const int* d_other
 
 template <int M8, bool USER, int EPI>
 void launch_gram(const GramArgs& a, int sms, cudaStream_t s) {
-    const int m = a.n + 1;
-    const size_t smem = sizeof(double) * GRAM_WARPS * (static_cast<size_t>(m) * gram_ld(m) + 2 * a.n);
     auto kern = k_gram<M8, USER, EPI>;
-    static size_t cached_smem = 0;
     static int per_sm = 0;
-    if (cached_smem != smem) {
-        MRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
-        MRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GRAM_WARPS * 32, smem));
-        cached_smem = smem;
-    }
+    if (per_sm == 0)
+        MRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GRAM_WARPS * 32, 0));
     MRB_REQUIRE(per_sm >= 1, "gram kernel does not fit on an SM");
+    // persistent CTAs: one wave that fills every SM, work items handed out dynamically
     const int grid = std::min(sms * per_sm, ceil_div(a.n_work, GRAM_WARPS));
-    kern<<<grid > 0 ? grid : 1, GRAM_WARPS * 32, smem, s>>>(a);
+    kern<<<grid > 0 ? grid : 1, GRAM_WARPS * 32, 0, s>>>(a);
     MRB_CUDA(cudaGetLastError());
 }
 
@@ -408,6 +550,7 @@ struct AlsProblem::GramState {
     DevBuf<double> partials;
     DevBuf<int> counters;      // [0] work counter, [1..] segment arrival counters
     DevBuf<double> sse_partials;
+    DevBuf<double> sse_owner;  // per-item residual sum of squares from the factorisation
     int sms = 148;
     int st_doubles = 0;
 };
@@ -430,9 +573,9 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
         g.partials.alloc(static_cast<size_t>(std::max(slots, 1)) * g.st_doubles);
         g.counters.alloc(1 + static_cast<size_t>(std::max(std::max(g.user.n_multi, g.item.n_multi), 1)));
         g.sse_partials.alloc(1024);
+        g.sse_owner.alloc(static_cast<size_t>(std::max(ni_, 1)));
     }
     GramState& g = *gram_;
-    std::vector<double> h_sse(1024);
 
     auto half = [&](bool user_side) {
         Side& sd = user_side ? g.user : g.item;
@@ -450,6 +593,12 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
         a.x = user_side ? uf_.p : itf_.p;
         a.partials = g.partials.p;
         a.seg_done = g.counters.p + 1;
+        if (!user_side) {
+            // every rating belongs to exactly one item, so the per-item residuals of the item
+            // half-sweep add up to the training SSE after the sweep -- for free
+            MRB_CUDA(cudaMemsetAsync(g.sse_owner.p, 0, sizeof(double) * g.sse_owner.n, s_));
+            a.sse_out = g.sse_owner.p;
+        }
         if (sd.n_work == 0) return;
         if (user_side) dispatch_gram<true, EPI_SOLVE>(a, g.sms, s_);
         else dispatch_gram<false, EPI_SOLVE>(a, g.sms, s_);
@@ -463,14 +612,11 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
         half(false);
         // rr := sum of squared training errors (the exact solve leaves no normal-equation
         // residual to monitor); same relative-decrease rule as matrix.cpp:871-875.
-        k_sse_partials<<<1024, 256, 0, s_>>>(user_ids_.p, item_ids_.p, ratings_.p, uf_.p, itf_.p, k_,
-                                             nnz_, g.sse_partials.p);
+        k_sum_fixed<<<1, 1024, 0, s_>>>(g.sse_owner.p, ni_, g.sse_partials.p);
         MRB_CUDA(cudaGetLastError());
-        MRB_CUDA(cudaMemcpyAsync(h_sse.data(), g.sse_partials.p, sizeof(double) * 1024,
-                                 cudaMemcpyDeviceToHost, s_));
-        MRB_CUDA(cudaStreamSynchronize(s_));
         double rr = 0;
-        for (double v : h_sse) rr += v;
+        MRB_CUDA(cudaMemcpyAsync(&rr, g.sse_partials.p, sizeof(double), cudaMemcpyDeviceToHost, s_));
+        MRB_CUDA(cudaStreamSynchronize(s_));
         info.sweeps_run++;
         info.last_rr = rr;
         if (sweep >= 3) {
