@@ -110,6 +110,8 @@ typedef struct mrb_als_run_info {
     double last_rr;        /* item-solve normal-equation residual of the last sweep */
     float device_ms;       /* CUDA-event time of the sweep loop on the problem's stream */
     float index_build_ms;  /* CUDA-event time of the two stable groupings at creation */
+    float gram_ms;         /* CUDA-event time summed over the gather-Gram kernel launches */
+    int kernel_launches;   /* kernels launched by the sweep loop */
 } mrb_als_run_info;
 
 MRB_API int mrb_als_create(const int* user_ids, const int* item_ids, int num_ratings,

@@ -20,7 +20,8 @@ class AlsRunInfo(ctypes.Structure):
     """mrb_als_run_info (include/cpp_ls_b200.h)."""
     _fields_ = [("sweeps_returned", ctypes.c_int), ("sweeps_run", ctypes.c_int),
                 ("cg_iterations", ctypes.c_int), ("last_rr", ctypes.c_double),
-                ("device_ms", ctypes.c_float), ("index_build_ms", ctypes.c_float)]
+                ("device_ms", ctypes.c_float), ("index_build_ms", ctypes.c_float),
+                ("gram_ms", ctypes.c_float), ("kernel_launches", ctypes.c_int)]
 
 
 class CppLsError(RuntimeError):

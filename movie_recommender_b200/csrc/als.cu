@@ -47,8 +47,8 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
     DevBuf<int> bad(1);
     MRB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s_));
     if (nnz > 0) {
-        k_check_ids<<<ceil_div(nnz, 256), 256, 0, s_>>>(user_ids_.p, nnz, nu_, bad.p);
-        k_check_ids<<<ceil_div(nnz, 256), 256, 0, s_>>>(item_ids_.p, nnz, ni_, bad.p);
+        k_check_ids<<<ceil_div(nnz, 256), 256, 0, s_>>>(user_ids_.p, nnz, nu_, bad.p); MRB_LAUNCHED(1);
+        k_check_ids<<<ceil_div(nnz, 256), 256, 0, s_>>>(item_ids_.p, nnz, ni_, bad.p); MRB_LAUNCHED(1);
     }
     int h_bad = 0;
     MRB_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s_));
@@ -91,6 +91,7 @@ AlsRunInfo AlsProblem::run(int algorithm, double min_r_decrease, int max_iterati
     MRB_CUDA(cudaEventCreate(&e0));
     MRB_CUDA(cudaEventCreate(&e1));
     MRB_CUDA(cudaEventRecord(e0, s_));
+    const long long launches0 = g_kernel_launches.load();
     AlsRunInfo info;
     if (algorithm == ALS_GRAM_CG || algorithm == ALS_GRAM_CHOLESKY)
         info = run_gram(algorithm, min_r_decrease, max_iteration);
@@ -99,6 +100,7 @@ AlsRunInfo AlsProblem::run(int algorithm, double min_r_decrease, int max_iterati
     MRB_CUDA(cudaEventRecord(e1, s_));
     MRB_CUDA(cudaEventSynchronize(e1));
     MRB_CUDA(cudaEventElapsedTime(&info.device_ms, e0, e1));
+    info.kernel_launches = static_cast<int>(g_kernel_launches.load() - launches0);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return info;
@@ -122,9 +124,11 @@ AlsRunInfo AlsProblem::run_faithful(int algorithm, double min_r_decrease, int ma
         // algorithm != 1: explicit-transpose CG on the very first sweep only (:824-827, :861-866)
         const int variant = (algorithm == ALS_REF_CG || sweep >= 1) ? 1 : 2;
         CgResult ur = user_cg.solve(user_op, ratings_.p, uf_.p, 0.01, 200, variant);   // :818
-        if (nnz_ > 0)
+        if (nnz_ > 0) {
             k_ratings_minus_bias<<<ceil_div(nnz_, 256), 256, 0, s_>>>(ratings_.p, user_ids_.p,
                                                                       uf_.p, n, nnz_, rmb_.p);
+            MRB_LAUNCHED(1);
+        }
         CgResult ir = item_cg.solve(item_op, rmb_.p, itf_.p, 0.01, 200, variant);      // :854
         info.cg_iterations += ur.iterations + ir.iterations;
         info.sweeps_run++;

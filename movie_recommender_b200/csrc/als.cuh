@@ -27,6 +27,8 @@ struct AlsRunInfo {
     int cg_iterations = 0;     // total inner CG iterations (CG modes)
     double last_rr = 0;        // item-solve normal-equation residual of the last sweep
     float device_ms = 0;       // CUDA-event time of the sweep loop on the problem's stream
+    float gram_ms = 0;         // CUDA-event time summed over the k_gram launches (algorithms 3, 4)
+    int kernel_launches = 0;   // kernels launched by the sweep loop
 };
 
 class AlsProblem {

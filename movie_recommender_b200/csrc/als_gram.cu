@@ -52,13 +52,18 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// element j of the augmented row [a; b]
+// Element j of the augmented row [a; b] AS FETCHED: no arithmetic on a value that has just been
+// requested from memory (a dependent instruction right behind the load would stall the warp
+// before the current step's DMMAs are issued and defeat the prefetch).  On the item side
+// element k is fetched as the raw user bias; the caller turns it into rating - bias at use time.
 template <bool USER>
 __device__ __forceinline__ double aug_elem(const double* __restrict__ row, double rating, int j,
                                            int k) {
-    if (j < k) return row[j];
-    if (USER) return j == k ? 1.0 : (j == k + 1 ? rating : 0.0);
-    return j == k ? rating - row[k] : 0.0;
+    if (USER) {
+        if (j < k) return row[j];
+        return j == k ? 1.0 : (j == k + 1 ? rating : 0.0);
+    }
+    return j <= k ? row[j] : 0.0;
 }
 
 struct GramArgs {
@@ -313,43 +318,46 @@ k_gram(const GramArgs A) {
 #pragma unroll
         for (int t = 0; t < ST; t++) { acc[t][0] = 0; acc[t][1] = 0; }
 
+        // Fragments are fetched TWO k-steps ahead of their use (f -> f1 -> f2), ids/ratings a
+        // whole 32-rating batch ahead, so that an HBM miss (user factors do not fit L2 entirely)
+        // has ~2 x 28 DMMA issue times to land.
         const int cnt = wi.end - wi.beg;
         const int nsteps = (cnt + 3) >> 2;
         int ids_cur = 0, ids_nxt = 0;
         double rts_cur = 0, rts_nxt = 0;
         if (lane < cnt) { ids_cur = A.other_g[wi.beg + lane]; rts_cur = A.rating_g[wi.beg + lane]; }
         if (32 + lane < cnt) { ids_nxt = A.other_g[wi.beg + 32 + lane]; rts_nxt = A.rating_g[wi.beg + 32 + lane]; }
-        double f_next[M8];
-        {
-            const int id = __shfl_sync(0xffffffffu, ids_cur, q);
-            const double rt = shfl_double(rts_cur, q);
-            const bool valid = q < cnt;
+        auto fetch = [&](double (&dst)[M8], double& rt_out, int st, int batch_of_cur) {
+            // fragments of k-step `st` (ratings 4 st .. 4 st + 3); st's batch is the current or next
+            const bool from_next = (st >> 3) != batch_of_cur;
+            const int src = ((st & 7) << 2) + q;
+            const int id = __shfl_sync(0xffffffffu, from_next ? ids_nxt : ids_cur, src);
+            const double rt = shfl_double(from_next ? rts_nxt : rts_cur, src);
+            const bool valid = (st << 2) + q < cnt;
             const double* row = A.other_f + static_cast<size_t>(id) * A.other_stride;
 #pragma unroll
-            for (int t = 0; t < M8; t++) f_next[t] = valid ? aug_elem<USER>(row, rt, t * 8 + p, k) : 0.0;
-        }
+            for (int t = 0; t < M8; t++) dst[t] = valid ? aug_elem<USER>(row, rt, t * 8 + p, k) : 0.0;
+            rt_out = valid ? rt : 0.0;
+        };
+        double f1[M8], f2[M8], rt1 = 0, rt2 = 0;
+        fetch(f1, rt1, 0, 0);
+        fetch(f2, rt2, 1, 0);
+        const bool bias_lane = !USER && p == (k & 7);   // index k lives in the last tile (k>>3 == M8-1)
         for (int step = 0; step < nsteps; step++) {
             double f[M8];
 #pragma unroll
-            for (int t = 0; t < M8; t++) f[t] = f_next[t];
-            const int ns = step + 1;
-            if (ns < nsteps) {
-                if ((ns & 7) == 0) {
-                    ids_cur = ids_nxt;
-                    rts_cur = rts_nxt;
-                    const int e = (ns << 2) + 32 + lane;
-                    ids_nxt = 0;
-                    rts_nxt = 0;
-                    if (e < cnt) { ids_nxt = A.other_g[wi.beg + e]; rts_nxt = A.rating_g[wi.beg + e]; }
-                }
-                const int src = ((ns & 7) << 2) + q;
-                const int id = __shfl_sync(0xffffffffu, ids_cur, src);
-                const double rt = shfl_double(rts_cur, src);
-                const bool valid = (ns << 2) + q < cnt;
-                const double* row = A.other_f + static_cast<size_t>(id) * A.other_stride;
-#pragma unroll
-                for (int t = 0; t < M8; t++) f_next[t] = valid ? aug_elem<USER>(row, rt, t * 8 + p, k) : 0.0;
+            for (int t = 0; t < M8; t++) { f[t] = f1[t]; f1[t] = f2[t]; }
+            if (bias_lane) f[M8 - 1] = rt1 - f[M8 - 1];   // b = rating - user bias (matrix.cpp:1029)
+            rt1 = rt2;
+            if ((step & 7) == 0 && step > 0) {
+                ids_cur = ids_nxt;
+                rts_cur = rts_nxt;
+                const int e = (step << 2) + 32 + lane;
+                ids_nxt = 0;
+                rts_nxt = 0;
+                if (e < cnt) { ids_nxt = A.other_g[wi.beg + e]; rts_nxt = A.rating_g[wi.beg + e]; }
             }
+            if (step + 2 < nsteps) fetch(f2, rt2, step + 2, step >> 3);
 #pragma unroll
             for (int ti = 0; ti < M8; ti++)
 #pragma unroll
@@ -471,9 +479,11 @@ void build_side(Side& sd, const int* d_ptr, const int* d_idx, const int* d_other
                 const double* d_ratings, int owners, int nnz, cudaStream_t s) {
     sd.other_g.alloc(nnz);
     sd.rating_g.alloc(nnz);
-    if (nnz)
+    if (nnz) {
         k_gather_grouped<<<ceil_div(nnz, 256), 256, 0, s>>>(d_idx, d_other_ids, d_ratings, nnz,
                                                             sd.other_g.p, sd.rating_g.p);
+        MRB_LAUNCHED(1);
+    }
     MRB_CUDA(cudaGetLastError());
     std::vector<int> ptr(static_cast<size_t>(owners) + 1);
     MRB_CUDA(cudaMemcpyAsync(ptr.data(), d_ptr, sizeof(int) * ptr.size(), cudaMemcpyDeviceToHost, s));
@@ -523,7 +533,7 @@ void launch_gram(const GramArgs& a, int sms, cudaStream_t s) {
     MRB_REQUIRE(per_sm >= 1, "gram kernel does not fit on an SM");
     // persistent CTAs: one wave that fills every SM, work items handed out dynamically
     const int grid = std::min(sms * per_sm, ceil_div(a.n_work, GRAM_WARPS));
-    kern<<<grid > 0 ? grid : 1, GRAM_WARPS * 32, 0, s>>>(a);
+    kern<<<grid > 0 ? grid : 1, GRAM_WARPS * 32, 0, s>>>(a); MRB_LAUNCHED(1);
     MRB_CUDA(cudaGetLastError());
 }
 
@@ -577,6 +587,7 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
     }
     GramState& g = *gram_;
 
+    std::vector<cudaEvent_t> ev;   // (start, stop) per k_gram launch
     auto half = [&](bool user_side) {
         Side& sd = user_side ? g.user : g.item;
         MRB_CUDA(cudaMemsetAsync(g.counters.p, 0, sizeof(int) * g.counters.n, s_));
@@ -600,8 +611,15 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
             a.sse_out = g.sse_owner.p;
         }
         if (sd.n_work == 0) return;
+        cudaEvent_t e0, e1;
+        MRB_CUDA(cudaEventCreate(&e0));
+        MRB_CUDA(cudaEventCreate(&e1));
+        MRB_CUDA(cudaEventRecord(e0, s_));
         if (user_side) dispatch_gram<true, EPI_SOLVE>(a, g.sms, s_);
         else dispatch_gram<false, EPI_SOLVE>(a, g.sms, s_);
+        MRB_CUDA(cudaEventRecord(e1, s_));
+        ev.push_back(e0);
+        ev.push_back(e1);
     };
 
     AlsRunInfo info;
@@ -612,7 +630,7 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
         half(false);
         // rr := sum of squared training errors (the exact solve leaves no normal-equation
         // residual to monitor); same relative-decrease rule as matrix.cpp:871-875.
-        k_sum_fixed<<<1, 1024, 0, s_>>>(g.sse_owner.p, ni_, g.sse_partials.p);
+        k_sum_fixed<<<1, 1024, 0, s_>>>(g.sse_owner.p, ni_, g.sse_partials.p); MRB_LAUNCHED(1);
         MRB_CUDA(cudaGetLastError());
         double rr = 0;
         MRB_CUDA(cudaMemcpyAsync(&rr, g.sse_partials.p, sizeof(double), cudaMemcpyDeviceToHost, s_));
@@ -627,6 +645,14 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
         sweep++;
     }
     info.sweeps_returned = sweep;
+    MRB_CUDA(cudaStreamSynchronize(s_));
+    for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+        float ms = 0;
+        MRB_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+        info.gram_ms += ms;
+        cudaEventDestroy(ev[i]);
+        cudaEventDestroy(ev[i + 1]);
+    }
     return info;
 }
 

@@ -226,6 +226,8 @@ int mrb_als_run(mrb_als_problem* p, int algorithm, double min_r_decrease, int ma
             info->last_rr = r.last_rr;
             info->device_ms = r.device_ms;
             info->index_build_ms = p->impl.index_build_ms();
+            info->gram_ms = r.gram_ms;
+            info->kernel_launches = r.kernel_launches;
         }
         return r.sweeps_returned;
     });

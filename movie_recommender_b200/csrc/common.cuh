@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -84,6 +85,10 @@ struct PinnedBuf {
     PinnedBuf& operator=(const PinnedBuf&) = delete;
     ~PinnedBuf() { if (p) cudaFreeHost(p); }
 };
+
+// Number of kernels this library has launched (what bench.py reports as gpu_launches).
+inline std::atomic<long long> g_kernel_launches{0};
+#define MRB_LAUNCHED(n) (::mrb::g_kernel_launches.fetch_add((n), std::memory_order_relaxed))
 
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 

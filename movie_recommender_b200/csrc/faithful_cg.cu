@@ -155,9 +155,9 @@ CgResult FaithfulCG::solve(FaithfulOp& A, const double* d_b, double* d_x, double
     A.tmul(d_b, b2_.p, bounds, nchunks, s_);       // b2 = A^T b      (matrix.cpp:465 / :549)
     A.mul(d_x, tmp_.p, s_);                        // tmp = A x       (:469)
     A.tmul(tmp_.p, Ap_.p, bounds, nchunks, s_);    // Ap = A^T tmp    (:470)
-    k_residual_init<<<vb, 256, 0, s_>>>(Ap_.p, b2_.p, r_.p, p_.p, cols_);
-    k_dot_partials<<<T_, DOT_THREADS, 0, s_>>>(r_.p, r_.p, col_bounds_.p, partials_.p, nullptr);
-    k_cg_init<<<1, 1, 0, s_>>>(st, partials_.p, T_, min_r_decrease, max_iteration);
+    k_residual_init<<<vb, 256, 0, s_>>>(Ap_.p, b2_.p, r_.p, p_.p, cols_); MRB_LAUNCHED(1);
+    k_dot_partials<<<T_, DOT_THREADS, 0, s_>>>(r_.p, r_.p, col_bounds_.p, partials_.p, nullptr); MRB_LAUNCHED(1);
+    k_cg_init<<<1, 1, 0, s_>>>(st, partials_.p, T_, min_r_decrease, max_iteration); MRB_LAUNCHED(1);
     MRB_CUDA(cudaGetLastError());
 
     // Iterations are enqueued in small batches; every kernel is a no-op once `done` is set on
@@ -171,12 +171,12 @@ CgResult FaithfulCG::solve(FaithfulOp& A, const double* d_b, double* d_x, double
         for (int i = 0; i < batch; i++) {
             A.mul(p_.p, tmp_.p, s_);                        // :493
             A.tmul(tmp_.p, Ap_.p, bounds, nchunks, s_);     // :494
-            k_dot_partials<<<T_, DOT_THREADS, 0, s_>>>(p_.p, Ap_.p, col_bounds_.p, partials_.p, st);
-            k_cg_alpha<<<1, 1, 0, s_>>>(st, partials_.p, T_);
-            k_update_xr<<<vb, 256, 0, s_>>>(st, d_x, r_.p, p_.p, Ap_.p, cols_);
-            k_dot_partials<<<T_, DOT_THREADS, 0, s_>>>(r_.p, r_.p, col_bounds_.p, partials_.p, st);
-            k_cg_beta<<<1, 1, 0, s_>>>(st, partials_.p, T_);
-            k_update_p<<<vb, 256, 0, s_>>>(st, r_.p, p_.p, cols_);
+            k_dot_partials<<<T_, DOT_THREADS, 0, s_>>>(p_.p, Ap_.p, col_bounds_.p, partials_.p, st); MRB_LAUNCHED(1);
+            k_cg_alpha<<<1, 1, 0, s_>>>(st, partials_.p, T_); MRB_LAUNCHED(1);
+            k_update_xr<<<vb, 256, 0, s_>>>(st, d_x, r_.p, p_.p, Ap_.p, cols_); MRB_LAUNCHED(1);
+            k_dot_partials<<<T_, DOT_THREADS, 0, s_>>>(r_.p, r_.p, col_bounds_.p, partials_.p, st); MRB_LAUNCHED(1);
+            k_cg_beta<<<1, 1, 0, s_>>>(st, partials_.p, T_); MRB_LAUNCHED(1);
+            k_update_p<<<vb, 256, 0, s_>>>(st, r_.p, p_.p, cols_); MRB_LAUNCHED(1);
         }
         MRB_CUDA(cudaGetLastError());
     }
@@ -254,14 +254,14 @@ CsrFaithfulOp::CsrFaithfulOp(int rows_in, int cols_in, int nnz, const int* d_row
 
 void CsrFaithfulOp::mul(const double* d_x, double* d_y, cudaStream_t s) {
     if (rows == 0) return;
-    k_csr_mul<<<ceil_div(rows, 256), 256, 0, s>>>(rowptr_, colidx_, vals_, d_x, d_y, rows, guard);
+    k_csr_mul<<<ceil_div(rows, 256), 256, 0, s>>>(rowptr_, colidx_, vals_, d_x, d_y, rows, guard); MRB_LAUNCHED(1);
 }
 
 void CsrFaithfulOp::tmul(const double* d_t, double* d_y, const int* d_row_bounds, int /*nchunks*/,
                          cudaStream_t s) {
     if (cols == 0) return;
     k_csc_tmul<<<ceil_div(static_cast<long long>(cols) * 32, 256), 256, 0, s>>>(
-        t_ptr_.p, t_row_.p, t_val_.p, d_t, d_y, cols, d_row_bounds, guard);
+        t_ptr_.p, t_row_.p, t_val_.p, d_t, d_y, cols, d_row_bounds, guard); MRB_LAUNCHED(1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -404,7 +404,7 @@ void AlsFaithfulOp::mul(const double* d_x, double* d_y, cudaStream_t s) {
         attr_set = true;
     }
     k_als_mul<<<ceil_div(rows, AM_WARPS * 32), AM_WARPS * 32, smem, s>>>(
-        owner_, other_, other_f_, d_x, d_y, rows, width_, other_stride_, k_, guard);
+        owner_, other_, other_f_, d_x, d_y, rows, width_, other_stride_, k_, guard); MRB_LAUNCHED(1);
 }
 
 void AlsFaithfulOp::tmul(const double* d_t, double* d_y, const int* d_row_bounds, int /*nchunks*/,
@@ -425,6 +425,7 @@ void AlsFaithfulOp::tmul(const double* d_t, double* d_y, const int* d_row_bounds
         case 7: MRB_TMUL(7); break;
         default: MRB_TMUL(8); break;
     }
+    MRB_LAUNCHED(1);
 #undef MRB_TMUL
 }
 

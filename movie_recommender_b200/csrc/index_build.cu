@@ -67,15 +67,15 @@ void exclusive_scan_i32(const int* d_in, int* d_out, long long n, cudaStream_t s
     if (n <= 0) return;
     const int tiles = ceil_div(n, SCAN_TILE);
     if (tiles == 1) {
-        k_scan_tile<<<1, SCAN_THREADS, 0, s>>>(d_in, d_out, nullptr, n);
+        k_scan_tile<<<1, SCAN_THREADS, 0, s>>>(d_in, d_out, nullptr, n); MRB_LAUNCHED(1);
         MRB_CUDA(cudaGetLastError());
         return;
     }
     DevBuf<int> sums(tiles);
-    k_scan_tile<<<tiles, SCAN_THREADS, 0, s>>>(d_in, d_out, sums.p, n);
+    k_scan_tile<<<tiles, SCAN_THREADS, 0, s>>>(d_in, d_out, sums.p, n); MRB_LAUNCHED(1);
     MRB_CUDA(cudaGetLastError());
     exclusive_scan_i32(sums.p, sums.p, tiles, s);
-    k_add_tile_offsets<<<ceil_div(n, 256), 256, 0, s>>>(d_out, sums.p, n);
+    k_add_tile_offsets<<<ceil_div(n, 256), 256, 0, s>>>(d_out, sums.p, n); MRB_LAUNCHED(1);
     MRB_CUDA(cudaGetLastError());
     MRB_CUDA(cudaStreamSynchronize(s));  // `sums` is freed on return
 }
@@ -193,7 +193,7 @@ void stable_group_by(const int* d_key, int n, int num_groups, int* d_ptr, int* d
     MRB_CUDA(cudaMemsetAsync(d_ptr, 0, sizeof(int) * (static_cast<size_t>(num_groups) + 1), s));
     if (n == 0) return;
     MRB_REQUIRE(num_groups > 0, "stable_group_by: items but no groups");
-    k_count_keys<<<ceil_div(n, 256), 256, 0, s>>>(d_key, n, d_ptr);
+    k_count_keys<<<ceil_div(n, 256), 256, 0, s>>>(d_key, n, d_ptr); MRB_LAUNCHED(1);
     MRB_CUDA(cudaGetLastError());
     exclusive_scan_i32(d_ptr, d_ptr, static_cast<long long>(num_groups) + 1, s);
 
@@ -201,7 +201,7 @@ void stable_group_by(const int* d_key, int n, int num_groups, int* d_ptr, int* d
     while (bits < 31 && (1LL << bits) < num_groups) bits++;
     const int passes = bits == 0 ? 0 : (bits + 7) / 8;
     if (passes == 0) {  // a single group: identity order
-        k_iota<<<ceil_div(n, 256), 256, 0, s>>>(d_idx, n);
+        k_iota<<<ceil_div(n, 256), 256, 0, s>>>(d_idx, n); MRB_LAUNCHED(1);
         MRB_CUDA(cudaGetLastError());
         return;
     }
@@ -217,11 +217,11 @@ void stable_group_by(const int* d_key, int n, int num_groups, int* d_ptr, int* d
     for (int p = 0; p < passes; p++) {
         int* kout = kbuf[p & 1];
         int* vout = ((passes - 1 - p) & 1) ? val_b.p : d_idx;
-        k_radix_hist<<<num_blocks, RS_THREADS, 0, s>>>(kin, n, 8 * p, hist.p, num_blocks);
+        k_radix_hist<<<num_blocks, RS_THREADS, 0, s>>>(kin, n, 8 * p, hist.p, num_blocks); MRB_LAUNCHED(1);
         MRB_CUDA(cudaGetLastError());
         exclusive_scan_i32(hist.p, hist.p, static_cast<long long>(256) * num_blocks, s);
         k_radix_scatter<<<num_blocks, RS_THREADS, 0, s>>>(kin, vin, n, 8 * p, hist.p, num_blocks,
-                                                           kout, vout);
+                                                           kout, vout); MRB_LAUNCHED(1);
         MRB_CUDA(cudaGetLastError());
         kin = kout;
         vin = vout;
@@ -260,10 +260,10 @@ void csr_transpose(int rows, int cols, int nnz, const int* d_rowptr, const int* 
     }
     DevBuf<int> idx(nnz), row_of(nnz);
     stable_group_by(d_colidx, nnz, cols, d_t_ptr, idx.p, s);
-    k_expand_rows<<<ceil_div(rows, 256), 256, 0, s>>>(d_rowptr, rows, row_of.p);
+    k_expand_rows<<<ceil_div(rows, 256), 256, 0, s>>>(d_rowptr, rows, row_of.p); MRB_LAUNCHED(1);
     MRB_CUDA(cudaGetLastError());
     k_gather_transposed<<<ceil_div(nnz, 256), 256, 0, s>>>(idx.p, row_of.p, d_vals, nnz, d_t_row,
-                                                          d_t_val);
+                                                          d_t_val); MRB_LAUNCHED(1);
     MRB_CUDA(cudaGetLastError());
     MRB_CUDA(cudaStreamSynchronize(s));
 }
