@@ -125,6 +125,43 @@ MRB_API int mrb_als_run(mrb_als_problem* p, int algorithm, double min_r_decrease
                 mrb_als_run_info* info);
 MRB_API void mrb_als_destroy(mrb_als_problem* p);
 
+/* ------------------------------------------------------------------------------------------
+ * 5. Extensions: multi-GPU, one process per GPU.
+ *    Users, then movies, are row-partitioned in nnz-balanced contiguous ranges; each rank holds
+ *    full replicas of both factor matrices.  The exact-solve kernel (algorithm 4) stores every
+ *    solved row into all replicas through NVLink peer pointers, i.e. the all-gather of the factor
+ *    shards is fused into the producing kernel; the caller only needs a stream-ordered barrier
+ *    between half-sweeps (bench: a one-element NCCL all-reduce).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Host-only: bounds[0..world] = first owner of each rank's range, from a CSR pointer array. */
+MRB_API int mrb_shard_ranges(const int* ptr, int owners, int world, int* bounds);
+/* Restricts the problem to rank's row ranges and builds its work lists. */
+MRB_API int mrb_als_set_shard(mrb_als_problem* p, int rank, int world);
+/* out4 = {user_lo, user_hi, item_lo, item_hi}. */
+MRB_API int mrb_als_get_shard_ranges(mrb_als_problem* p, int* out4);
+/* Raw device pointers of the two factor matrices (for an NCCL exchange by the caller). */
+MRB_API int mrb_als_device_factors(mrb_als_problem* p, void** d_user_factors, void** d_item_factors);
+/* CUDA IPC handles (64 bytes each) of this rank's factor replicas ... */
+MRB_API int mrb_als_ipc_handles(mrb_als_problem* p, unsigned char* user_handle64,
+                                unsigned char* item_handle64);
+/* ... and their counterpart: map every other rank's replicas (handles concatenated by rank). */
+MRB_API int mrb_als_open_peers(mrb_als_problem* p, const unsigned char* user_handles,
+                               const unsigned char* item_handles, int world, int rank);
+/* Same, from device pointers that are already valid in this process (replicas on the same GPU
+ * or on peers with access enabled); entry `rank` is ignored. */
+MRB_API int mrb_als_set_peer_pointers(mrb_als_problem* p, void* const* d_user_factor_replicas,
+                                      void* const* d_item_factor_replicas, int world);
+/* One exact half-sweep (user_side != 0: users) over this rank's rows, enqueued on `stream`
+ * (a cudaStream_t); does not synchronise. */
+MRB_API int mrb_als_half_sweep(mrb_als_problem* p, int user_side, void* stream);
+/* Sum of this rank's per-movie residuals of the last movie half-sweep (synchronises stream). */
+MRB_API int mrb_als_shard_sse(mrb_als_problem* p, void* stream, double* out);
+/* CUDA-event time (ms) summed over the half-sweep launches since the last call. */
+MRB_API int mrb_als_collect_gram_ms(mrb_als_problem* p, float* out);
+/* Kernels launched by this library in this process so far. */
+MRB_API long long mrb_kernel_launches(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,30 @@ def _declare(dll):
     dll.mrb_als_run.argtypes = [c_void_p, c_int, c_double, c_int, ctypes.POINTER(AlsRunInfo)]
     dll.mrb_als_destroy.restype = None
     dll.mrb_als_destroy.argtypes = [c_void_p]
+    _B = ctypes.POINTER(ctypes.c_ubyte)
+    dll.mrb_shard_ranges.restype = c_int
+    dll.mrb_shard_ranges.argtypes = [_I, c_int, c_int, _I]
+    dll.mrb_als_set_shard.restype = c_int
+    dll.mrb_als_set_shard.argtypes = [c_void_p, c_int, c_int]
+    dll.mrb_als_get_shard_ranges.restype = c_int
+    dll.mrb_als_get_shard_ranges.argtypes = [c_void_p, _I]
+    dll.mrb_als_device_factors.restype = c_int
+    dll.mrb_als_device_factors.argtypes = [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]
+    dll.mrb_als_ipc_handles.restype = c_int
+    dll.mrb_als_ipc_handles.argtypes = [c_void_p, _B, _B]
+    dll.mrb_als_open_peers.restype = c_int
+    dll.mrb_als_open_peers.argtypes = [c_void_p, _B, _B, c_int, c_int]
+    dll.mrb_als_set_peer_pointers.restype = c_int
+    dll.mrb_als_set_peer_pointers.argtypes = [c_void_p, ctypes.POINTER(c_void_p),
+                                              ctypes.POINTER(c_void_p), c_int]
+    dll.mrb_als_half_sweep.restype = c_int
+    dll.mrb_als_half_sweep.argtypes = [c_void_p, c_int, c_void_p]
+    dll.mrb_als_shard_sse.restype = c_int
+    dll.mrb_als_shard_sse.argtypes = [c_void_p, c_void_p, _D]
+    dll.mrb_als_collect_gram_ms.restype = c_int
+    dll.mrb_als_collect_gram_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
+    dll.mrb_kernel_launches.restype = ctypes.c_longlong
+    dll.mrb_kernel_launches.argtypes = []
     return dll
 
 

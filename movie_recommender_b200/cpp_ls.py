@@ -179,6 +179,65 @@ class AlsProblem:
         return info
 
 
+    # ---- multi-GPU extension (include/cpp_ls_b200.h section 5)
+    def set_shard(self, rank, world):
+        """Restrict the problem to this rank's nnz-balanced row ranges (builds the work lists)."""
+        _lib.check(_dll.mrb_als_set_shard(self._h, rank, world))
+        out = numpy.zeros(4, dtype=numpy.int32)
+        _lib.check(_dll.mrb_als_get_shard_ranges(self._h, _lib.ip(out)))
+        return tuple(int(v) for v in out)   # user_lo, user_hi, item_lo, item_hi
+
+    def device_factors(self):
+        """Raw device pointers (user_factors, item_factors)."""
+        u, i = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(_dll.mrb_als_device_factors(self._h, ctypes.byref(u), ctypes.byref(i)))
+        return u.value, i.value
+
+    def ipc_handles(self):
+        hu = (ctypes.c_ubyte * 64)()
+        hi = (ctypes.c_ubyte * 64)()
+        _lib.check(_dll.mrb_als_ipc_handles(self._h, hu, hi))
+        return bytes(hu), bytes(hi)
+
+    def open_peers(self, user_handles, item_handles, rank):
+        world = len(user_handles)
+        bu = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(user_handles))
+        bi = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(item_handles))
+        _lib.check(_dll.mrb_als_open_peers(self._h, bu, bi, world, rank))
+
+    def set_peer_pointers(self, user_ptrs, item_ptrs):
+        world = len(user_ptrs)
+        au = (ctypes.c_void_p * world)(*user_ptrs)
+        ai = (ctypes.c_void_p * world)(*item_ptrs)
+        _lib.check(_dll.mrb_als_set_peer_pointers(self._h, au, ai, world))
+
+    def half_sweep(self, user_side, stream):
+        _lib.check(_dll.mrb_als_half_sweep(self._h, 1 if user_side else 0, ctypes.c_void_p(stream)))
+
+    def shard_sse(self, stream):
+        out = ctypes.c_double(0)
+        _lib.check(_dll.mrb_als_shard_sse(self._h, ctypes.c_void_p(stream),
+                                          ctypes.cast(ctypes.byref(out), _lib._D)))
+        return out.value
+
+    def collect_gram_ms(self):
+        out = ctypes.c_float(0)
+        _lib.check(_dll.mrb_als_collect_gram_ms(self._h, ctypes.byref(out)))
+        return out.value
+
+
+def shard_ranges(ptr, world):
+    """nnz-balanced contiguous row ranges (host only): bounds[0..world] from a CSR pointer array."""
+    ptr = numpy.ascontiguousarray(ptr, dtype=numpy.int32)
+    bounds = numpy.zeros(world + 1, dtype=numpy.int32)
+    _lib.check(_dll.mrb_shard_ranges(_lib.ip(ptr), len(ptr) - 1, world, _lib.ip(bounds)))
+    return bounds
+
+
+def kernel_launches():
+    return int(_dll.mrb_kernel_launches())
+
+
 def group_by(keys, num_groups):
     """Stable grouping on the GPU (K4): returns (ptr[num_groups+1], idx[n])."""
     keys = numpy.ascontiguousarray(keys, dtype=numpy.int32)

@@ -8,6 +8,7 @@
 // The reference's materialised nnz x (k+1) matrices (17 GB each at ML-27M, k=50) never exist.
 #pragma once
 #include <memory>
+#include <vector>
 
 #include "common.cuh"
 #include "faithful_cg.cuh"
@@ -31,6 +32,9 @@ struct AlsRunInfo {
     int kernel_launches = 0;   // kernels launched by the sweep loop
 };
 
+// bounds[0..world]: nnz-balanced contiguous owner ranges from a CSR pointer array (host).
+void balanced_ranges(const int* ptr, int owners, int world, int* bounds);
+
 class AlsProblem {
 public:
     // Host pointers; uploads and builds both groupings (K4).
@@ -43,6 +47,22 @@ public:
 
     // Runs the sweep loop of matrix.cpp:814-890 on the device-resident problem.
     AlsRunInfo run(int algorithm, double min_r_decrease, int max_iteration, int thread_count);
+
+    // ---- multi-GPU: users, then movies, are row-partitioned in nnz-balanced
+    // contiguous ranges over `world` ranks; every rank keeps full replicas of both factor
+    // matrices.  The solve kernel stores each solved row into EVERY replica (peer pointers over
+    // NVLink), so the all-gather of the factor shards is fused into the producing kernel.
+    void set_shard(int rank, int world);
+    void shard_ranges(int* user_lo, int* user_hi, int* item_lo, int* item_hi) const;
+    // peer replicas of the factor matrices, index = rank (entry `rank` may be the local buffer)
+    void set_peers(const std::vector<double*>& user_factor_peers,
+                   const std::vector<double*>& item_factor_peers);
+    // One exact (algorithm 4) half-sweep over this rank's rows, enqueued on `stream`.
+    void half_sweep(bool user_side, cudaStream_t stream);
+    void half_sweep_prepare() { ensure_gram(); }   // builds this rank's work lists
+    // Sum of this rank's per-row residuals of the last item half-sweep (after a sync).
+    double shard_sse(cudaStream_t stream);
+    float collect_gram_ms();   // CUDA-event time of the half_sweep launches since the last call
 
     int nnz() const { return nnz_; }
     int k() const { return k_; }
@@ -60,12 +80,17 @@ public:
 private:
     AlsRunInfo run_faithful(int algorithm, double min_r_decrease, int max_iteration, int T);
     AlsRunInfo run_gram(int algorithm, double min_r_decrease, int max_iteration);
+    void ensure_gram();
+    void launch_half(bool user_side, cudaStream_t stream);
 
     int nnz_, k_, nu_, ni_;
     cudaStream_t s_ = nullptr;
     DevBuf<int> user_ids_, item_ids_, u_ptr_, u_idx_, i_ptr_, i_idx_;
     DevBuf<double> ratings_, uf_, itf_, rmb_;
     float index_ms_ = 0;
+    int rank_ = 0, world_ = 1;
+    std::vector<double*> uf_peers_, itf_peers_;
+    std::vector<cudaEvent_t> gram_events_;
     struct GramState;
     std::shared_ptr<GramState> gram_;  // shared_ptr: deleter bound where GramState is complete (als_gram.cu)
 };

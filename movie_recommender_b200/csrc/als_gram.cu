@@ -82,6 +82,8 @@ struct GramArgs {
     double* G_out;            // EPI_STORE: [owner][n*n]
     double* g_out;            // EPI_STORE: [owner][n]
     double* sse_out;          // optional [owner]: sum of squared residuals after the solve
+    double* x_peers[8];       // other replicas of the owner factor matrix (NVLink peer memory)
+    int n_peers;              // number of entries of x_peers (0 on a single GPU)
 };
 
 enum { EPI_SOLVE = 0, EPI_STORE = 1 };
@@ -120,7 +122,7 @@ __device__ __forceinline__ double xor_sum_q(double v) {   // sum over the 4 lane
 template <int M8>
 __device__ __forceinline__ void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], int n,
                                            double* __restrict__ xo, double* __restrict__ sse_slot,
-                                           int lane) {
+                                           int lane, const GramArgs& A, size_t row_offset) {
     constexpr int TN = M8 - 1;            // tile row/column holding index n (the rhs)
     const int p = lane >> 2, q = lane & 3;
     const int pr = n & 7;
@@ -293,7 +295,12 @@ __device__ __forceinline__ void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], 
 #pragma unroll
             for (int s = 0; s < 2; s++) {
                 const int c = 8 * t + 2 * q + s;
-                if (c < n) xo[c] = xq[t][s] + dl[t][s];
+                if (c < n) {
+                    const double v = xq[t][s] + dl[t][s];
+                    xo[c] = v;
+                    // fused all-gather: the solved row goes into every peer replica as well
+                    for (int j = 0; j < A.n_peers; j++) A.x_peers[j][row_offset + c] = v;
+                }
             }
     }
 }
@@ -412,7 +419,8 @@ k_gram(const GramArgs A) {
             continue;
         }
         gram_solve<M8>(acc, n, A.x + static_cast<size_t>(wi.owner) * n,
-                       A.sse_out ? A.sse_out + wi.owner : nullptr, lane);
+                       A.sse_out ? A.sse_out + wi.owner : nullptr, lane, A,
+                       static_cast<size_t>(wi.owner) * n);
     }
 }
 
@@ -466,6 +474,25 @@ __global__ void k_gather_grouped(const int* __restrict__ idx, const int* __restr
     rating_g[e] = ratings[r];
 }
 
+}  // namespace
+
+// bounds[r] = first owner of rank r: contiguous ranges holding ~nnz/world ratings each.
+void balanced_ranges(const int* ptr, int owners, int world, int* bounds) {
+    const long long nnz = ptr[owners];
+    bounds[0] = 0;
+    int o = 0;
+    for (int r = 1; r < world; r++) {
+        const long long target = nnz * r / world;
+        while (o < owners && ptr[o] < target) o++;
+        // the boundary nearest to the target (never before the previous boundary)
+        if (o > bounds[r - 1] && target - ptr[o - 1] < ptr[o] - target) o--;
+        bounds[r] = o;
+    }
+    bounds[world] = owners;
+}
+
+namespace {
+
 struct Side {
     DevBuf<int> other_g;
     DevBuf<double> rating_g;
@@ -473,10 +500,11 @@ struct Side {
     int n_work = 0;
     int n_multi = 0;
     int n_slots = 0;
+    int lo = 0, hi = 0;   // owner range of this rank
 };
 
 void build_side(Side& sd, const int* d_ptr, const int* d_idx, const int* d_other_ids,
-                const double* d_ratings, int owners, int nnz, cudaStream_t s) {
+                const double* d_ratings, int owners, int nnz, int rank, int world, cudaStream_t s) {
     sd.other_g.alloc(nnz);
     sd.rating_g.alloc(nnz);
     if (nnz) {
@@ -488,14 +516,19 @@ void build_side(Side& sd, const int* d_ptr, const int* d_idx, const int* d_other
     std::vector<int> ptr(static_cast<size_t>(owners) + 1);
     MRB_CUDA(cudaMemcpyAsync(ptr.data(), d_ptr, sizeof(int) * ptr.size(), cudaMemcpyDeviceToHost, s));
     MRB_CUDA(cudaStreamSynchronize(s));
+    // this rank's contiguous, nnz-balanced owner range
+    std::vector<int> bounds(static_cast<size_t>(world) + 1);
+    balanced_ranges(ptr.data(), owners, world, bounds.data());
+    sd.lo = bounds[rank];
+    sd.hi = bounds[rank + 1];
     // longest-processing-time-first order: owners by descending degree (stable)
-    std::vector<int> order(owners);
-    std::iota(order.begin(), order.end(), 0);
+    std::vector<int> order(static_cast<size_t>(sd.hi - sd.lo));
+    std::iota(order.begin(), order.end(), sd.lo);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b];
     });
     std::vector<WorkItem> work;
-    work.reserve(owners + nnz / GRAM_SEG + 1);
+    work.reserve(order.size() + nnz / GRAM_SEG + 1);
     sd.n_multi = 0;
     sd.n_slots = 0;
     for (int o : order) {
@@ -563,78 +596,138 @@ struct AlsProblem::GramState {
     DevBuf<double> sse_owner;  // per-item residual sum of squares from the factorisation
     int sms = 148;
     int st_doubles = 0;
+    int built_rank = -1, built_world = -1;
 };
+
+void AlsProblem::ensure_gram() {
+    const int n_u = k_ + 1;
+    const int m8 = (n_u + 1 + 7) / 8;
+    MRB_REQUIRE(m8 <= 7, "als algorithm 3/4: rank above 54 is not supported yet");
+    if (gram_ && gram_->built_rank == rank_ && gram_->built_world == world_) return;
+    gram_ = std::make_shared<GramState>();
+    GramState& g = *gram_;
+    int dev = 0;
+    MRB_CUDA(cudaGetDevice(&dev));
+    MRB_CUDA(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, dev));
+    build_side(g.user, u_ptr_.p, u_idx_.p, item_ids_.p, ratings_.p, nu_, nnz_, rank_, world_, s_);
+    build_side(g.item, i_ptr_.p, i_idx_.p, user_ids_.p, ratings_.p, ni_, nnz_, rank_, world_, s_);
+    g.st_doubles = m8 * (m8 + 1) / 2 * 64;
+    const int slots = std::max(g.user.n_slots, g.item.n_slots);
+    g.partials.alloc(static_cast<size_t>(std::max(slots, 1)) * g.st_doubles);
+    g.counters.alloc(1 + static_cast<size_t>(std::max(std::max(g.user.n_multi, g.item.n_multi), 1)));
+    g.sse_partials.alloc(1024);
+    g.sse_owner.alloc(static_cast<size_t>(std::max(ni_, 1)));
+    g.built_rank = rank_;
+    g.built_world = world_;
+}
+
+// One k_gram launch (algorithm 4) over this rank's rows of one side, timed by a pair of events.
+void AlsProblem::launch_half(bool user_side, cudaStream_t stream) {
+    GramState& g = *gram_;
+    Side& sd = user_side ? g.user : g.item;
+    MRB_CUDA(cudaMemsetAsync(g.counters.p, 0, sizeof(int) * g.counters.n, stream));
+    GramArgs a{};
+    a.work = sd.work.p;
+    a.n_work = sd.n_work;
+    a.work_counter = g.counters.p;
+    a.other_g = sd.other_g.p;
+    a.rating_g = sd.rating_g.p;
+    a.other_f = user_side ? itf_.p : uf_.p;
+    a.other_stride = user_side ? k_ : k_ + 1;
+    a.k = k_;
+    a.n = user_side ? k_ + 1 : k_;
+    a.x = user_side ? uf_.p : itf_.p;
+    a.partials = g.partials.p;
+    a.seg_done = g.counters.p + 1;
+    a.n_peers = 0;
+    const std::vector<double*>& peers = user_side ? uf_peers_ : itf_peers_;
+    for (size_t j = 0; j < peers.size(); j++)
+        if (static_cast<int>(j) != rank_ && peers[j] != nullptr && a.n_peers < 8)
+            a.x_peers[a.n_peers++] = peers[j];
+    if (!user_side) {
+        // every rating belongs to exactly one item, so the per-item residuals of the item
+        // half-sweep add up to the training SSE after the sweep -- for free
+        MRB_CUDA(cudaMemsetAsync(g.sse_owner.p, 0, sizeof(double) * g.sse_owner.n, stream));
+        a.sse_out = g.sse_owner.p;
+    }
+    if (sd.n_work == 0) return;
+    cudaEvent_t e0, e1;
+    MRB_CUDA(cudaEventCreate(&e0));
+    MRB_CUDA(cudaEventCreate(&e1));
+    MRB_CUDA(cudaEventRecord(e0, stream));
+    if (user_side) dispatch_gram<true, EPI_SOLVE>(a, g.sms, stream);
+    else dispatch_gram<false, EPI_SOLVE>(a, g.sms, stream);
+    MRB_CUDA(cudaEventRecord(e1, stream));
+    gram_events_.push_back(e0);
+    gram_events_.push_back(e1);
+}
+
+float AlsProblem::collect_gram_ms() {
+    float total = 0;
+    for (size_t i = 0; i + 1 < gram_events_.size(); i += 2) {
+        float ms = 0;
+        MRB_CUDA(cudaEventSynchronize(gram_events_[i + 1]));
+        MRB_CUDA(cudaEventElapsedTime(&ms, gram_events_[i], gram_events_[i + 1]));
+        total += ms;
+        cudaEventDestroy(gram_events_[i]);
+        cudaEventDestroy(gram_events_[i + 1]);
+    }
+    gram_events_.clear();
+    return total;
+}
+
+void AlsProblem::set_shard(int rank, int world) {
+    MRB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "als: bad shard (rank, world)");
+    rank_ = rank;
+    world_ = world;
+}
+
+void AlsProblem::shard_ranges(int* user_lo, int* user_hi, int* item_lo, int* item_hi) const {
+    MRB_REQUIRE(gram_ != nullptr, "als: shard_ranges before the work lists were built");
+    *user_lo = gram_->user.lo;
+    *user_hi = gram_->user.hi;
+    *item_lo = gram_->item.lo;
+    *item_hi = gram_->item.hi;
+}
+
+void AlsProblem::set_peers(const std::vector<double*>& user_factor_peers,
+                           const std::vector<double*>& item_factor_peers) {
+    uf_peers_ = user_factor_peers;
+    itf_peers_ = item_factor_peers;
+}
+
+void AlsProblem::half_sweep(bool user_side, cudaStream_t stream) {
+    ensure_gram();
+    launch_half(user_side, stream);
+}
+
+double AlsProblem::shard_sse(cudaStream_t stream) {
+    ensure_gram();
+    GramState& g = *gram_;
+    k_sum_fixed<<<1, 1024, 0, stream>>>(g.sse_owner.p, ni_, g.sse_partials.p);
+    MRB_LAUNCHED(1);
+    MRB_CUDA(cudaGetLastError());
+    double rr = 0;
+    MRB_CUDA(cudaMemcpyAsync(&rr, g.sse_partials.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    MRB_CUDA(cudaStreamSynchronize(stream));
+    return rr;
+}
 
 AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_iteration) {
     MRB_REQUIRE(algorithm == ALS_GRAM_CHOLESKY, "als: algorithm 3 not built yet");
-    const int n_u = k_ + 1, n_i = k_;
-    const int m8 = (n_u + 1 + 7) / 8;
-    MRB_REQUIRE(m8 <= 7, "als algorithm 3/4: rank above 54 is not supported yet");
-    if (!gram_) {
-        gram_ = std::make_shared<GramState>();
-        GramState& g = *gram_;
-        int dev = 0;
-        MRB_CUDA(cudaGetDevice(&dev));
-        MRB_CUDA(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, dev));
-        build_side(g.user, u_ptr_.p, u_idx_.p, item_ids_.p, ratings_.p, nu_, nnz_, s_);
-        build_side(g.item, i_ptr_.p, i_idx_.p, user_ids_.p, ratings_.p, ni_, nnz_, s_);
-        g.st_doubles = m8 * (m8 + 1) / 2 * 64;
-        const int slots = std::max(g.user.n_slots, g.item.n_slots);
-        g.partials.alloc(static_cast<size_t>(std::max(slots, 1)) * g.st_doubles);
-        g.counters.alloc(1 + static_cast<size_t>(std::max(std::max(g.user.n_multi, g.item.n_multi), 1)));
-        g.sse_partials.alloc(1024);
-        g.sse_owner.alloc(static_cast<size_t>(std::max(ni_, 1)));
-    }
-    GramState& g = *gram_;
-
-    std::vector<cudaEvent_t> ev;   // (start, stop) per k_gram launch
-    auto half = [&](bool user_side) {
-        Side& sd = user_side ? g.user : g.item;
-        MRB_CUDA(cudaMemsetAsync(g.counters.p, 0, sizeof(int) * g.counters.n, s_));
-        GramArgs a{};
-        a.work = sd.work.p;
-        a.n_work = sd.n_work;
-        a.work_counter = g.counters.p;
-        a.other_g = sd.other_g.p;
-        a.rating_g = sd.rating_g.p;
-        a.other_f = user_side ? itf_.p : uf_.p;
-        a.other_stride = user_side ? k_ : k_ + 1;
-        a.k = k_;
-        a.n = user_side ? n_u : n_i;
-        a.x = user_side ? uf_.p : itf_.p;
-        a.partials = g.partials.p;
-        a.seg_done = g.counters.p + 1;
-        if (!user_side) {
-            // every rating belongs to exactly one item, so the per-item residuals of the item
-            // half-sweep add up to the training SSE after the sweep -- for free
-            MRB_CUDA(cudaMemsetAsync(g.sse_owner.p, 0, sizeof(double) * g.sse_owner.n, s_));
-            a.sse_out = g.sse_owner.p;
-        }
-        if (sd.n_work == 0) return;
-        cudaEvent_t e0, e1;
-        MRB_CUDA(cudaEventCreate(&e0));
-        MRB_CUDA(cudaEventCreate(&e1));
-        MRB_CUDA(cudaEventRecord(e0, s_));
-        if (user_side) dispatch_gram<true, EPI_SOLVE>(a, g.sms, s_);
-        else dispatch_gram<false, EPI_SOLVE>(a, g.sms, s_);
-        MRB_CUDA(cudaEventRecord(e1, s_));
-        ev.push_back(e0);
-        ev.push_back(e1);
-    };
-
+    MRB_REQUIRE(world_ == 1, "als: run() drives one GPU; a sharded problem is driven half-sweep by "
+                             "half-sweep (mrb_als_half_sweep) with an exchange in between");
+    ensure_gram();
+    collect_gram_ms();
     AlsRunInfo info;
     int sweep = 0;
     double old_rr = 0;
     while (sweep < max_iteration) {
-        half(true);
-        half(false);
+        launch_half(true, s_);
+        launch_half(false, s_);
         // rr := sum of squared training errors (the exact solve leaves no normal-equation
         // residual to monitor); same relative-decrease rule as matrix.cpp:871-875.
-        k_sum_fixed<<<1, 1024, 0, s_>>>(g.sse_owner.p, ni_, g.sse_partials.p); MRB_LAUNCHED(1);
-        MRB_CUDA(cudaGetLastError());
-        double rr = 0;
-        MRB_CUDA(cudaMemcpyAsync(&rr, g.sse_partials.p, sizeof(double), cudaMemcpyDeviceToHost, s_));
-        MRB_CUDA(cudaStreamSynchronize(s_));
+        const double rr = shard_sse(s_);
         info.sweeps_run++;
         info.last_rr = rr;
         if (sweep >= 3) {
@@ -646,13 +739,7 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
     }
     info.sweeps_returned = sweep;
     MRB_CUDA(cudaStreamSynchronize(s_));
-    for (size_t i = 0; i + 1 < ev.size(); i += 2) {
-        float ms = 0;
-        MRB_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
-        info.gram_ms += ms;
-        cudaEventDestroy(ev[i]);
-        cudaEventDestroy(ev[i + 1]);
-    }
+    info.gram_ms = collect_gram_ms();
     return info;
 }
 

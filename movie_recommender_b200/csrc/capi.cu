@@ -166,8 +166,12 @@ int mrb_csr_transpose(int rows, int cols, const int* rowptr, const int* colidx, 
 
 struct mrb_als_problem {
     AlsProblem impl;
+    std::vector<void*> opened;   // cudaIpcOpenMemHandle mappings to close
     mrb_als_problem(const int* u, const int* i, int nnz, const double* r, int k, int nu, int ni)
         : impl(u, i, nnz, r, k, nu, ni) {}
+    ~mrb_als_problem() {
+        for (void* q : opened) cudaIpcCloseMemHandle(q);
+    }
 };
 
 int mrb_als_create(const int* user_ids, const int* item_ids, int num_ratings,
@@ -234,5 +238,122 @@ int mrb_als_run(mrb_als_problem* p, int algorithm, double min_r_decrease, int ma
 }
 
 void mrb_als_destroy(mrb_als_problem* p) { delete p; }
+
+int mrb_shard_ranges(const int* ptr, int owners, int world, int* bounds) {
+    return guarded([&] {
+        MRB_REQUIRE(ptr != nullptr && bounds != nullptr && owners >= 0 && world >= 1,
+                    "mrb_shard_ranges: bad arguments");
+        balanced_ranges(ptr, owners, world, bounds);
+        return 0;
+    });
+}
+
+int mrb_als_set_shard(mrb_als_problem* p, int rank, int world) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        p->impl.set_shard(rank, world);
+        p->impl.half_sweep_prepare();
+        return 0;
+    });
+}
+
+int mrb_als_get_shard_ranges(mrb_als_problem* p, int* out4) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr && out4 != nullptr, "null argument");
+        p->impl.shard_ranges(&out4[0], &out4[1], &out4[2], &out4[3]);
+        return 0;
+    });
+}
+
+int mrb_als_device_factors(mrb_als_problem* p, void** d_user_factors, void** d_item_factors) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        *d_user_factors = p->impl.user_factors();
+        *d_item_factors = p->impl.item_factors();
+        return 0;
+    });
+}
+
+int mrb_als_ipc_handles(mrb_als_problem* p, unsigned char* user_handle64,
+                        unsigned char* item_handle64) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        cudaIpcMemHandle_t hu, hi;
+        MRB_CUDA(cudaIpcGetMemHandle(&hu, p->impl.user_factors()));
+        MRB_CUDA(cudaIpcGetMemHandle(&hi, p->impl.item_factors()));
+        std::memcpy(user_handle64, &hu, 64);
+        std::memcpy(item_handle64, &hi, 64);
+        return 0;
+    });
+}
+
+int mrb_als_open_peers(mrb_als_problem* p, const unsigned char* user_handles,
+                       const unsigned char* item_handles, int world, int rank) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr && world >= 1 && world <= 8 && rank >= 0 && rank < world,
+                    "mrb_als_open_peers: bad arguments");
+        std::vector<double*> up(world, nullptr), ip(world, nullptr);
+        for (int r = 0; r < world; r++) {
+            if (r == rank) {
+                up[r] = p->impl.user_factors();
+                ip[r] = p->impl.item_factors();
+                continue;
+            }
+            cudaIpcMemHandle_t hu, hi;
+            std::memcpy(&hu, user_handles + 64 * r, 64);
+            std::memcpy(&hi, item_handles + 64 * r, 64);
+            void* q = nullptr;
+            MRB_CUDA(cudaIpcOpenMemHandle(&q, hu, cudaIpcMemLazyEnablePeerAccess));
+            p->opened.push_back(q);
+            up[r] = static_cast<double*>(q);
+            MRB_CUDA(cudaIpcOpenMemHandle(&q, hi, cudaIpcMemLazyEnablePeerAccess));
+            p->opened.push_back(q);
+            ip[r] = static_cast<double*>(q);
+        }
+        p->impl.set_peers(up, ip);
+        return 0;
+    });
+}
+
+int mrb_als_set_peer_pointers(mrb_als_problem* p, void* const* d_user_factor_replicas,
+                              void* const* d_item_factor_replicas, int world) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr && world >= 1 && world <= 8, "mrb_als_set_peer_pointers: bad arguments");
+        std::vector<double*> up(world), ip(world);
+        for (int r = 0; r < world; r++) {
+            up[r] = static_cast<double*>(d_user_factor_replicas[r]);
+            ip[r] = static_cast<double*>(d_item_factor_replicas[r]);
+        }
+        p->impl.set_peers(up, ip);
+        return 0;
+    });
+}
+
+int mrb_als_half_sweep(mrb_als_problem* p, int user_side, void* stream) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        p->impl.half_sweep(user_side != 0, static_cast<cudaStream_t>(stream));
+        return 0;
+    });
+}
+
+int mrb_als_shard_sse(mrb_als_problem* p, void* stream, double* out) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr && out != nullptr, "null argument");
+        *out = p->impl.shard_sse(static_cast<cudaStream_t>(stream));
+        return 0;
+    });
+}
+
+int mrb_als_collect_gram_ms(mrb_als_problem* p, float* out) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr && out != nullptr, "null argument");
+        *out = p->impl.collect_gram_ms();
+        return 0;
+    });
+}
+
+long long mrb_kernel_launches(void) { return g_kernel_launches.load(); }
 
 }  // extern "C"

@@ -1,0 +1,114 @@
+"""Multi-GPU ALS: one process per GPU, ``torch.distributed`` for the
+plumbing (rendezvous, the stream-ordered barrier, max-over-ranks timing), hand-written CUDA for
+everything on the data path.
+
+Partitioning: users, then movies, are cut into ``world`` contiguous row ranges holding ~nnz/world
+ratings each; every rank keeps the whole COO, both groupings and full replicas of both factor
+matrices (C3: 2 GB per GPU), only the WORK is sharded.  Exchange: the one place the path shards is
+the all-gather of the freshly solved factor rows after each half-sweep.  Two implementations:
+
+* ``exchange="p2p"`` (default, the product): the solve kernel stores every solved row into all
+  replicas through NVLink peer pointers (CUDA IPC mappings of the other ranks' buffers), i.e. the
+  all-gather is fused into the producing kernel and overlaps the math row by row; between
+  half-sweeps only a one-element NCCL all-reduce remains, as a stream-ordered barrier.
+* ``exchange="nccl"`` (the baseline it is compared with): rows are written locally and the ranges
+  are exchanged with ``torch.distributed.all_gather`` on tensors aliasing the library's buffers.
+"""
+import numpy as np
+
+from . import cpp_ls
+
+
+class _DevArray:
+    """Wraps a raw device pointer for torch.as_tensor via __cuda_array_interface__."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+class ShardedAls:
+    def __init__(self, problem, k, num_users, num_items, rank, world, exchange="p2p"):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.k = rank, world, k
+        self.nu, self.ni = num_users, num_items
+        self.exchange = exchange
+        self.nnz = len(problem["ratings"])
+        self.prob = cpp_ls.AlsProblem(problem["user_ids"], problem["item_ids"], problem["ratings"],
+                                      k, num_users, num_items)
+        self.prob.set_factors(problem["user_factors0"], problem["item_factors0"])
+        self.ranges = self.prob.set_shard(rank, world)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.flag = torch.zeros(1, device=self.device)
+        if exchange == "p2p":
+            handles = [None] * world
+            dist.all_gather_object(handles, self.prob.ipc_handles())
+            self.prob.open_peers([h[0] for h in handles], [h[1] for h in handles], rank)
+        else:
+            pu, pi = self.prob.device_factors()
+            self.uf = torch.as_tensor(_DevArray(pu, num_users * (k + 1)), device=self.device)
+            self.itf = torch.as_tensor(_DevArray(pi, num_items * k), device=self.device)
+            all_ranges = [None] * world
+            dist.all_gather_object(all_ranges, self.ranges)
+            self.u_views = [self.uf[r[0] * (k + 1):r[1] * (k + 1)] for r in all_ranges]
+            self.i_views = [self.itf[r[2] * k:r[3] * k] for r in all_ranges]
+        dist.barrier()
+
+    def _exchange(self, user_side):
+        if self.exchange == "p2p":
+            # rows are already in every replica; wait until every rank's kernel has finished
+            self.dist.all_reduce(self.flag)
+        else:
+            views = self.u_views if user_side else self.i_views
+            self.dist.all_gather(views, views[self.rank])
+
+    def sweep(self):
+        stream = self.torch.cuda.current_stream().cuda_stream
+        self.prob.half_sweep(True, stream)
+        self._exchange(True)
+        self.prob.half_sweep(False, stream)
+        self._exchange(False)
+
+    def sse(self):
+        """Training sum of squared errors after the last sweep, summed over ranks."""
+        stream = self.torch.cuda.current_stream().cuda_stream
+        t = self.torch.tensor([self.prob.shard_sse(stream)], dtype=self.torch.float64,
+                              device=self.device)
+        self.dist.all_reduce(t)
+        return float(t.item())
+
+    def bench(self, algorithm, warmup, steps, sampler=None):
+        torch, dist = self.torch, self.dist
+        if algorithm != 4:
+            raise ValueError("the sharded path implements algorithm 4 (exact half-sweeps)")
+        for _ in range(warmup):
+            self.sweep()
+        self.prob.collect_gram_ms()
+        launches0 = cpp_ls.kernel_launches()
+        dist.barrier()
+        torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.start()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        import time
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            self.sweep()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        wall_ms = (time.time() - t0) * 1e3
+        clocks = sampler.stop() if sampler is not None else None
+        ms = torch.tensor([e0.elapsed_time(e1), self.prob.collect_gram_ms()], dtype=torch.float64,
+                          device=self.device)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)     # device time = max over ranks
+        launches = cpp_ls.kernel_launches() - launches0
+        sse = self.sse()
+        uf, itf = self.prob.get_factors()
+        return dict(device_ms=float(ms[0]), gram_ms=float(ms[1]), wall_ms=wall_ms, clocks=clocks,
+                    launches=int(launches) * self.world, user_factors=uf, item_factors=itf,
+                    sse=sse, exchange=self.exchange, ranges=self.ranges)

@@ -1,0 +1,60 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size-2 gloo processes agree on row ranges
+that tile the rows and balance the ratings (the data-path kernels need GPUs; the N > 1 GPU run is
+tests/test_gpu_sharded.py / bench.py --gpus N)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from conftest import ROOT
+from movie_recommender_b200 import cpp_ls, synth
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, %r)
+from movie_recommender_b200 import cpp_ls, synth
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+u, i = synth.rating_pairs(3000, 700, 90000, 11, 10, seed=5)
+uptr = np.concatenate([[0], np.cumsum(np.bincount(u, minlength=3000))]).astype(np.int32)
+iptr = np.concatenate([[0], np.cumsum(np.bincount(i, minlength=700))]).astype(np.int32)
+ub, ib = cpp_ls.shard_ranges(uptr, world), cpp_ls.shard_ranges(iptr, world)
+mine = (int(ub[rank]), int(ub[rank + 1]), int(ib[rank]), int(ib[rank + 1]))
+allr = [None] * world
+dist.all_gather_object(allr, mine)
+# ranges tile the rows in rank order
+assert allr[0][0] == 0 and allr[-1][1] == 3000 and allr[0][2] == 0 and allr[-1][3] == 700
+for a, b in zip(allr[:-1], allr[1:]):
+    assert a[1] == b[0] and a[3] == b[2]
+# every rank's share of the ratings is within 5 %% of nnz / world
+for r in allr:
+    assert abs((uptr[r[1]] - uptr[r[0]]) - 90000 / world) < 0.05 * 90000
+    assert abs((iptr[r[3]] - iptr[r[2]]) - 90000 / world) < 0.05 * 90000
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok", mine)
+'''
+
+
+def test_shard_ranges_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+                          "29517", str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2
+
+
+def test_shard_ranges_edge_cases():
+    ptr = np.array([0, 5, 5, 9, 20, 21, 40], dtype=np.int32)
+    assert list(cpp_ls.shard_ranges(ptr, 1)) == [0, 6]
+    b = cpp_ls.shard_ranges(ptr, 3)
+    assert b[0] == 0 and b[-1] == 6 and np.all(np.diff(b) >= 0)
+    empty = np.zeros(4, dtype=np.int32)                       # three rows, no ratings
+    assert list(cpp_ls.shard_ranges(empty, 2))[0] == 0
+    assert list(cpp_ls.shard_ranges(np.array([0], dtype=np.int32), 4)) == [0, 0, 0, 0, 0]
