@@ -57,12 +57,19 @@ def load_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
@@ -77,7 +84,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -89,7 +96,12 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows
+        if self.t_begin is not None and self.t_end is not None:
+            # a sample is printed up to one period after it was taken
+            inside = [r for r in rows if self.t_begin <= r[0] <= self.t_end + 0.05]
+            rows = inside if inside else rows
+        for _, r in rows:
             if len(r) < 9:
                 continue
             try:
@@ -249,14 +261,16 @@ def main():
     if world == 1:
         prob = cpp_ls.AlsProblem(p["user_ids"], p["item_ids"], p["ratings"], k, nu, ni)
         prob.set_factors(p["user_factors0"], p["item_factors0"])
+        sampler.start()                                         # nvidia-smi needs ~0.3 s to start
         for _ in range(args.warmup):
             prob.run(args.algorithm, -1e300, 1)
         torch.cuda.synchronize()
-        sampler.start()
+        sampler.mark_begin()
         t0 = time.time()
         info = prob.run(args.algorithm, -1e300, args.steps)     # syncs its stream before returning
         torch.cuda.synchronize()
         wall_ms = (time.time() - t0) * 1e3
+        sampler.mark_end()
         clocks = sampler.stop()
         dev_ms = float(info.device_ms)
         gram_ms = float(getattr(info, "gram_ms", 0.0))

@@ -85,6 +85,21 @@ MRB_API const char* mrb_last_error(void);   /* message of the last failing call 
 MRB_API int mrb_device_count(void);         /* number of visible CUDA devices (0 if none / no driver) */
 MRB_API const char* mrb_build_info(void);   /* "sm_100a ..." */
 
+/* The generic sparse solver with a selectable algorithm: 1, 2 = the reference's two variants
+ * (bit-faithful, same as the drop-in symbols above); 3 = the same CG and stopping rule with
+ * GPU-native summation order (the fast path of the linear / bias model, config 2). */
+typedef struct mrb_ls_info {
+    int iterations;
+    double final_rr;
+    float transpose_ms;   /* algorithm 3: stable CSR -> CSC build, CUDA events */
+    float solve_ms;       /* algorithm 3: A^T b + CG loop, CUDA events */
+} mrb_ls_info;
+MRB_API int mrb_cg_least_squares(int A_rows, int A_cols, const int* A_row_indices,
+                                 const int* A_col_indices, const double* A_values, int b_length,
+                                 const double* b_values, int x_length, double* x_values,
+                                 double min_r_decrease, int max_iteration, int algorithm,
+                                 mrb_ls_info* info);
+
 /* ------------------------------------------------------------------------------------------
  * 3. Extensions: index build (K4), exposed for bit-exact parity tests.
  *    Replaces sparse_matrix_transpose and helpers (matrix.cpp:617-738, 251-297).

@@ -24,6 +24,12 @@ class AlsRunInfo(ctypes.Structure):
                 ("gram_ms", ctypes.c_float), ("kernel_launches", ctypes.c_int)]
 
 
+class LsInfo(ctypes.Structure):
+    """mrb_ls_info (include/cpp_ls_b200.h)."""
+    _fields_ = [("iterations", ctypes.c_int), ("final_rr", ctypes.c_double),
+                ("transpose_ms", ctypes.c_float), ("solve_ms", ctypes.c_float)]
+
+
 class CppLsError(RuntimeError):
     def __init__(self, code, message):
         super().__init__("cpp_ls_lib error %d: %s" % (code, message))
@@ -43,6 +49,9 @@ def _declare(dll):
     dll.als_from_python.restype = c_int
     dll.als_from_python.argtypes = [_I, _I, c_int, _D, c_int, c_int, _D, c_int, _D, c_double,
                                     c_int, c_int]
+    dll.mrb_cg_least_squares.restype = c_int
+    dll.mrb_cg_least_squares.argtypes = [c_int, c_int, _I, _I, _D, c_int, _D, c_int, _D, c_double,
+                                         c_int, c_int, ctypes.POINTER(LsInfo)]
     dll.mrb_last_error.restype = ctypes.c_char_p
     dll.mrb_last_error.argtypes = []
     dll.mrb_build_info.restype = ctypes.c_char_p

@@ -11,7 +11,8 @@ threaded C++ (``cpp/ls_lib``).  Differences, all deliberate:
   ``user_factors`` / ``item_factors``) so that a caller can be deterministic without touching
   the global NumPy RNG; when they are omitted the initial vectors are drawn from the global
   NumPy RNG with exactly the reference's calls (cpp_ls.py:92, :150-151).
-* ``algorithm`` accepts the extension values 3 and 4 for ``als`` (include/cpp_ls_b200.h).
+* ``algorithm`` accepts the extension values 3 and 4 for ``als`` and 3 for
+  ``cg_least_squares`` (include/cpp_ls_b200.h).
 * a failing native call raises ``CppLsError`` instead of terminating the process.
 """
 import ctypes
@@ -74,6 +75,15 @@ def cg_least_squares(A_row_indices: numpy.ndarray, A_col_indices: numpy.ndarray,
         x = numpy.array(x0, dtype=numpy.double).reshape(A_num_columns, 1)
     x_length = A_num_columns
 
+    if algorithm == 3:
+        # extension: same CG and stopping rule, GPU-native summation order (K3)
+        info = _lib.LsInfo()
+        iterations = _lib.check(_dll.mrb_cg_least_squares(
+            A_rows, A_num_columns, _lib.ip(A_row_indices), _lib.ip(A_col_indices),
+            _lib.dp(A_values), b_length, _lib.dp(b), x_length, _lib.dp(x),
+            ctypes.c_double(min_r_decrease), max_iterations, 3, ctypes.byref(info)))
+        cg_least_squares.last_info = info
+        return x, iterations, info.final_rr
     final_rr = ctypes.c_double(0)
     fn = _dll.cg_least_squares_from_python if algorithm == 1 else _dll.cg_least_squares2_from_python
     iterations = _lib.check(fn(

@@ -81,7 +81,7 @@ private:
     AlsRunInfo run_faithful(int algorithm, double min_r_decrease, int max_iteration, int T);
     AlsRunInfo run_gram(int algorithm, double min_r_decrease, int max_iteration);
     void ensure_gram();
-    void launch_half(bool user_side, cudaStream_t stream);
+    void launch_half(bool user_side, cudaStream_t stream, int epilogue);
 
     int nnz_, k_, nu_, ni_;
     cudaStream_t s_ = nullptr;
@@ -91,7 +91,10 @@ private:
     int rank_ = 0, world_ = 1;
     std::vector<double*> uf_peers_, itf_peers_;
     std::vector<cudaEvent_t> gram_events_;
+public:
     struct GramState;
+
+private:
     std::shared_ptr<GramState> gram_;  // shared_ptr: deleter bound where GramState is complete (als_gram.cu)
 };
 

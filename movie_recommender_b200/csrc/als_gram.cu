@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "als.cuh"
+#include "native_cg.cuh"
 
 namespace mrb {
 
@@ -588,6 +589,46 @@ void dispatch_gram(const GramArgs& a, int sms, cudaStream_t s) {
 
 }  // namespace
 
+
+namespace {
+// ------------------------------------------------------------------------------------------
+// K2a: the reference's CG (global alpha/beta, same stopping rule, matrix.cpp:456-529) on the
+// stored Gram blocks -- algorithm 3.  A^T A p is a block-diagonal matvec: one warp per owner reads
+// the n x n block row by row (coalesced; symmetric, so row j doubles as column j) -- HBM bound,
+// n*n*8 bytes per owner per iteration.  Sums are GPU-native but deterministic: per-owner partial
+// dots, then one fixed-order reduction.
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+k_block_matvec(const double* __restrict__ G, const double* __restrict__ v, double* __restrict__ out,
+               double* __restrict__ dots, int owners, int n, const CgState* __restrict__ guard) {
+    if (guard && guard->done) return;
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (o >= owners) return;
+    const int lane = threadIdx.x & 31;
+    const double* Go = G + static_cast<size_t>(o) * n * n;
+    const double* vo = v + static_cast<size_t>(o) * n;
+    const bool has0 = lane < n, has1 = lane + 32 < n;
+    const double v0 = has0 ? vo[lane] : 0.0, v1 = has1 ? vo[lane + 32] : 0.0;
+    double y0 = 0, y1 = 0;
+#pragma unroll 4
+    for (int j = 0; j < n; j++) {
+        const double vj = shfl_double(j < 32 ? v0 : v1, j & 31);
+        const double* row = Go + static_cast<size_t>(j) * n;
+        if (has0) y0 += row[lane] * vj;
+        if (has1) y1 += row[lane + 32] * vj;
+    }
+    double* oo = out + static_cast<size_t>(o) * n;
+    if (has0) oo[lane] = y0;
+    if (has1) oo[lane + 32] = y1;
+    double d = v0 * y0 + v1 * y1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+    if (lane == 0) dots[o] = d;
+}
+
+}  // namespace
+
 struct AlsProblem::GramState {
     Side user, item;
     DevBuf<double> partials;
@@ -597,6 +638,9 @@ struct AlsProblem::GramState {
     int sms = 148;
     int st_doubles = 0;
     int built_rank = -1, built_world = -1;
+    // algorithm 3 (Gram block-CG): stored blocks and CG vectors, sized for the larger side
+    DevBuf<double> G, g, r, p, Ap, dots, cg_partials;
+    DevBuf<FaithfulCG::State> cg_state;
 };
 
 void AlsProblem::ensure_gram() {
@@ -622,7 +666,7 @@ void AlsProblem::ensure_gram() {
 }
 
 // One k_gram launch (algorithm 4) over this rank's rows of one side, timed by a pair of events.
-void AlsProblem::launch_half(bool user_side, cudaStream_t stream) {
+void AlsProblem::launch_half(bool user_side, cudaStream_t stream, int epilogue) {
     GramState& g = *gram_;
     Side& sd = user_side ? g.user : g.item;
     MRB_CUDA(cudaMemsetAsync(g.counters.p, 0, sizeof(int) * g.counters.n, stream));
@@ -655,8 +699,19 @@ void AlsProblem::launch_half(bool user_side, cudaStream_t stream) {
     MRB_CUDA(cudaEventCreate(&e0));
     MRB_CUDA(cudaEventCreate(&e1));
     MRB_CUDA(cudaEventRecord(e0, stream));
-    if (user_side) dispatch_gram<true, EPI_SOLVE>(a, g.sms, stream);
-    else dispatch_gram<false, EPI_SOLVE>(a, g.sms, stream);
+    if (epilogue == EPI_STORE) {
+        // rows without ratings are not in the work list: their blocks must read as zero
+        const size_t owners = user_side ? nu_ : ni_;
+        MRB_CUDA(cudaMemsetAsync(g.G.p, 0, sizeof(double) * owners * a.n * a.n, stream));
+        MRB_CUDA(cudaMemsetAsync(g.g.p, 0, sizeof(double) * owners * a.n, stream));
+        a.G_out = g.G.p;
+        a.g_out = g.g.p;
+        if (user_side) dispatch_gram<true, EPI_STORE>(a, g.sms, stream);
+        else dispatch_gram<false, EPI_STORE>(a, g.sms, stream);
+    } else {
+        if (user_side) dispatch_gram<true, EPI_SOLVE>(a, g.sms, stream);
+        else dispatch_gram<false, EPI_SOLVE>(a, g.sms, stream);
+    }
     MRB_CUDA(cudaEventRecord(e1, stream));
     gram_events_.push_back(e0);
     gram_events_.push_back(e1);
@@ -698,7 +753,7 @@ void AlsProblem::set_peers(const std::vector<double*>& user_factor_peers,
 
 void AlsProblem::half_sweep(bool user_side, cudaStream_t stream) {
     ensure_gram();
-    launch_half(user_side, stream);
+    launch_half(user_side, stream, EPI_SOLVE);
 }
 
 double AlsProblem::shard_sse(cudaStream_t stream) {
@@ -713,21 +768,50 @@ double AlsProblem::shard_sse(cudaStream_t stream) {
     return rr;
 }
 
+// One reference-semantics CG solve on the stored blocks of one side (x in/out).
+static CgResult block_cg_solve(AlsProblem::GramState& g, double* x, int owners, int n,
+                               cudaStream_t s);
+
 AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_iteration) {
-    MRB_REQUIRE(algorithm == ALS_GRAM_CHOLESKY, "als: algorithm 3 not built yet");
     MRB_REQUIRE(world_ == 1, "als: run() drives one GPU; a sharded problem is driven half-sweep by "
                              "half-sweep (mrb_als_half_sweep) with an exchange in between");
     ensure_gram();
     collect_gram_ms();
+    GramState& g = *gram_;
     AlsRunInfo info;
     int sweep = 0;
     double old_rr = 0;
+    if (algorithm == ALS_GRAM_CG && g.G.n == 0) {
+        const size_t nu = nu_, ni = ni_, n_u = k_ + 1, n_i = k_;
+        const size_t blocks = std::max(nu * n_u * n_u, ni * n_i * n_i);
+        const size_t len = std::max(nu * n_u, ni * n_i);
+        g.G.alloc(std::max<size_t>(blocks, 1));
+        g.g.alloc(std::max<size_t>(len, 1));
+        g.r.alloc(std::max<size_t>(len, 1));
+        g.p.alloc(std::max<size_t>(len, 1));
+        g.Ap.alloc(std::max<size_t>(len, 1));
+        g.dots.alloc(std::max<size_t>(std::max(nu, ni), 1));
+        g.cg_partials.alloc(static_cast<size_t>(ceil_div(static_cast<long long>(len), 256)) + 1);
+        g.cg_state.alloc(1);
+    }
     while (sweep < max_iteration) {
-        launch_half(true, s_);
-        launch_half(false, s_);
-        // rr := sum of squared training errors (the exact solve leaves no normal-equation
-        // residual to monitor); same relative-decrease rule as matrix.cpp:871-875.
-        const double rr = shard_sse(s_);
+        double rr = 0;
+        if (algorithm == ALS_GRAM_CHOLESKY) {
+            launch_half(true, s_, EPI_SOLVE);
+            launch_half(false, s_, EPI_SOLVE);
+            // rr := sum of squared training errors (the exact solve leaves no normal-equation
+            // residual to monitor); same relative-decrease rule as matrix.cpp:871-875.
+            rr = shard_sse(s_);
+        } else {
+            // algorithm 3: build the blocks, then the reference's CG (always 0.01 / 200 inside
+            // als(), matrix.cpp:818, 854-855) with global alpha/beta over all owners
+            launch_half(true, s_, EPI_STORE);
+            CgResult ur = block_cg_solve(g, uf_.p, nu_, k_ + 1, s_);
+            launch_half(false, s_, EPI_STORE);
+            CgResult ir = block_cg_solve(g, itf_.p, ni_, k_, s_);
+            info.cg_iterations += ur.iterations + ir.iterations;
+            rr = ir.final_rr;
+        }
         info.sweeps_run++;
         info.last_rr = rr;
         if (sweep >= 3) {
@@ -741,6 +825,21 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
     MRB_CUDA(cudaStreamSynchronize(s_));
     info.gram_ms = collect_gram_ms();
     return info;
+}
+
+static CgResult block_cg_solve(AlsProblem::GramState& g, double* x, int owners, int n,
+                               cudaStream_t s) {
+    if (owners == 0) return CgResult();
+    const int len = owners * n;
+    const int mb = ceil_div(static_cast<long long>(owners) * 32, 256);
+    NativeCgWorkspace ws{g.r.p, g.p.p, g.Ap.p, g.dots.p, g.cg_partials.p, g.cg_state.p};
+    // A^T A v for the block-diagonal normal matrix; dots[o] = v_o . (G_o v_o)
+    auto apply = [&](const double* v, double* out, const CgState* guard) {
+        k_block_matvec<<<mb, 256, 0, s>>>(g.G.p, v, out, g.dots.p, owners, n, guard);
+        MRB_LAUNCHED(1);
+    };
+    // inside als() the inner solves always use (0.01, 200)            (matrix.cpp:818, 854-855)
+    return native_cg_solve(apply, g.g.p, x, len, owners, 0.01, 200, ws, s);
 }
 
 }  // namespace mrb

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "faithful_cg.cuh"
 #include "index_build.cuh"
+#include "ls_native.cuh"
 
 namespace mrb {
 static thread_local std::string g_last_error;
@@ -106,6 +107,38 @@ int als_from_python(int* user_ids, int* item_ids, int ratings_length, double* ra
         AlsRunInfo info = p.run(algorithm, min_r_decrease, max_iteration, g_thread_count);
         p.get_factors(user_factors_values, item_factors_values);
         return info.sweeps_returned;
+    });
+}
+
+int mrb_cg_least_squares(int A_rows, int A_cols, const int* A_row_indices,
+                         const int* A_col_indices, const double* A_values, int b_length,
+                         const double* b_values, int x_length, double* x_values,
+                         double min_r_decrease, int max_iteration, int algorithm,
+                         mrb_ls_info* info) {
+    return guarded([&] {
+        double rr = 0;
+        int it = 0;
+        mrb_ls_info out{};
+        if (algorithm == 3) {
+            MRB_REQUIRE(A_rows >= 0 && A_cols >= 0, "cg_least_squares: negative dimension");
+            MRB_REQUIRE(b_length == A_rows, "cg_least_squares: len(b) != rows of A");
+            MRB_REQUIRE(x_length == A_cols, "cg_least_squares: len(x) != columns of A");
+            LsNativeResult r = solve_ls_native(A_rows, A_cols, A_row_indices, A_col_indices,
+                                               A_values, b_values, x_values, min_r_decrease,
+                                               max_iteration);
+            it = r.iterations;
+            rr = r.final_rr;
+            out.transpose_ms = r.transpose_ms;
+            out.solve_ms = r.solve_ms;
+        } else {
+            it = solve_ls(algorithm == 1 ? 1 : 2, A_rows, A_cols, A_row_indices, A_col_indices,
+                          A_values, b_length, b_values, x_length, x_values, min_r_decrease,
+                          max_iteration, &rr);
+        }
+        out.iterations = it;
+        out.final_rr = rr;
+        if (info) *info = out;
+        return it;
     });
 }
 

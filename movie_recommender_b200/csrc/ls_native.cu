@@ -1,0 +1,145 @@
+// K3 -- the generic sparse least-squares solver (cpp_ls.cg_least_squares,
+// python/full_data/cpp_ls.py:47-111 -> cg_least_squares, cpp/ls_lib/matrix.cpp:456-529) with
+// GPU-native summation: the "linear model" path of config 2 (user + movie bias model, 2 non-zeros
+// per row).  Same algorithm and stopping rule as the reference; per CG iteration
+//   t  = A p      CSR, one thread per short row / one warp per long row
+//   Ap = A^T t    through the stable transpose built once by K4 (CSC), one warp per column,
+//                 fused with the per-column partial of p . Ap
+//   x, r, p updates fused with the partial sums of r . r
+// All HBM streaming; algorithmic bytes per iteration (nnz_A = non-zeros):
+//   2*nnz_A*(8+4) + (rows+cols+2)*4 + rows*8 + nnz_A*8 + 7*cols*8.
+#include "ls_native.cuh"
+
+#include "index_build.cuh"
+#include "native_cg.cuh"
+
+namespace mrb {
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+k_csr_mul_thread(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                 const double* __restrict__ vals, const double* __restrict__ x,
+                 double* __restrict__ y, int rows, const CgState* __restrict__ guard) {
+    if (guard && guard->done) return;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    double s = 0;
+    const int end = rowptr[r + 1];
+    for (int e = rowptr[r]; e < end; e++) s += vals[e] * x[colidx[e]];
+    y[r] = s;
+}
+
+__global__ void __launch_bounds__(256)
+k_csr_mul_warp(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+               const double* __restrict__ vals, const double* __restrict__ x,
+               double* __restrict__ y, int rows, const CgState* __restrict__ guard) {
+    if (guard && guard->done) return;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    double s = 0;
+    const int end = rowptr[r + 1];
+    for (int e = rowptr[r] + lane; e < end; e += 32) s += vals[e] * x[colidx[e]];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) y[r] = s;
+}
+
+// out[c] = sum over column c of val * t[row]; dots[c] = v[c] * out[c] (v may be null)
+__global__ void __launch_bounds__(256)
+k_csc_tmul_warp(const int* __restrict__ t_ptr, const int* __restrict__ t_row,
+                const double* __restrict__ t_val, const double* __restrict__ t,
+                const double* __restrict__ v, double* __restrict__ out, double* __restrict__ dots,
+                int cols, const CgState* __restrict__ guard) {
+    if (guard && guard->done) return;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= cols) return;
+    const int lane = threadIdx.x & 31;
+    const int beg = t_ptr[c], end = t_ptr[c + 1];
+    double s0 = 0, s1 = 0;
+    int e = beg + lane;
+    for (; e + 32 < end; e += 64) {
+        s0 += t_val[e] * t[t_row[e]];
+        s1 += t_val[e + 32] * t[t_row[e + 32]];
+    }
+    if (e < end) s0 += t_val[e] * t[t_row[e]];
+    double s = s0 + s1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) {
+        out[c] = s;
+        if (dots) dots[c] = v ? v[c] * s : 0.0;
+    }
+}
+
+}  // namespace
+
+LsNativeResult solve_ls_native(int rows, int cols, const int* rowptr, const int* colidx,
+                               const double* vals, const double* b, double* x,
+                               double min_r_decrease, int max_iteration) {
+    const int nnz = rowptr[rows];
+    cudaStream_t s;
+    MRB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{s};
+    DevBuf<int> d_rowptr(static_cast<size_t>(rows) + 1), d_col(nnz);
+    DevBuf<double> d_vals(nnz), d_b(rows), d_x(cols);
+    d_rowptr.upload(rowptr, static_cast<size_t>(rows) + 1, s);
+    d_col.upload(colidx, nnz, s);
+    d_vals.upload(vals, nnz, s);
+    d_b.upload(b, rows, s);
+    d_x.upload(x, cols, s);
+
+    cudaEvent_t e0, e1, e2;
+    MRB_CUDA(cudaEventCreate(&e0));
+    MRB_CUDA(cudaEventCreate(&e1));
+    MRB_CUDA(cudaEventCreate(&e2));
+    MRB_CUDA(cudaEventRecord(e0, s));
+    DevBuf<int> t_ptr(static_cast<size_t>(cols) + 1), t_row(nnz);
+    DevBuf<double> t_val(nnz);
+    csr_transpose(rows, cols, nnz, d_rowptr.p, d_col.p, d_vals.p, t_ptr.p, t_row.p, t_val.p, s);
+    MRB_CUDA(cudaEventRecord(e1, s));
+
+    const size_t len = std::max(cols, 1);
+    DevBuf<double> g(len), r(len), p(len), Ap(len), dots(len), tmp(std::max(rows, 1));
+    DevBuf<double> partials(static_cast<size_t>(ceil_div(static_cast<long long>(len), 256)) + 1);
+    DevBuf<CgState> state(1);
+    const bool long_rows = rows > 0 && nnz / rows > 8;
+    auto mul = [&](const double* v, double* out, const CgState* guard) {
+        if (rows == 0) return;
+        if (long_rows)
+            k_csr_mul_warp<<<ceil_div(static_cast<long long>(rows) * 32, 256), 256, 0, s>>>(
+                d_rowptr.p, d_col.p, d_vals.p, v, out, rows, guard);
+        else
+            k_csr_mul_thread<<<ceil_div(rows, 256), 256, 0, s>>>(d_rowptr.p, d_col.p, d_vals.p, v,
+                                                                 out, rows, guard);
+        MRB_LAUNCHED(1);
+    };
+    auto tmul = [&](const double* t, const double* v, double* out, double* dd, const CgState* guard) {
+        if (cols == 0) return;
+        k_csc_tmul_warp<<<ceil_div(static_cast<long long>(cols) * 32, 256), 256, 0, s>>>(
+            t_ptr.p, t_row.p, t_val.p, t, v, out, dd, cols, guard);
+        MRB_LAUNCHED(1);
+    };
+    tmul(d_b.p, nullptr, g.p, nullptr, nullptr);                    // g = A^T b   (matrix.cpp:465)
+    auto apply = [&](const double* v, double* out, const CgState* guard) {
+        mul(v, tmp.p, guard);
+        tmul(tmp.p, v, out, dots.p, guard);
+    };
+    NativeCgWorkspace ws{r.p, p.p, Ap.p, dots.p, partials.p, state.p};
+    CgResult cr = native_cg_solve(apply, g.p, d_x.p, cols, cols, min_r_decrease, max_iteration, ws, s);
+    MRB_CUDA(cudaEventRecord(e2, s));
+    d_x.download(x, cols, s);
+    MRB_CUDA(cudaStreamSynchronize(s));
+    LsNativeResult res;
+    res.iterations = cr.iterations;
+    res.final_rr = cr.final_rr;
+    MRB_CUDA(cudaEventElapsedTime(&res.transpose_ms, e0, e1));
+    MRB_CUDA(cudaEventElapsedTime(&res.solve_ms, e1, e2));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    return res;
+}
+
+}  // namespace mrb

@@ -83,6 +83,8 @@ class ShardedAls:
         torch, dist = self.torch, self.dist
         if algorithm != 4:
             raise ValueError("the sharded path implements algorithm 4 (exact half-sweeps)")
+        if sampler is not None:
+            sampler.start()
         for _ in range(warmup):
             self.sweep()
         self.prob.collect_gram_ms()
@@ -90,7 +92,7 @@ class ShardedAls:
         dist.barrier()
         torch.cuda.synchronize()
         if sampler is not None:
-            sampler.start()
+            sampler.mark_begin()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         import time
@@ -102,6 +104,8 @@ class ShardedAls:
         torch.cuda.synchronize()
         dist.barrier()
         wall_ms = (time.time() - t0) * 1e3
+        if sampler is not None:
+            sampler.mark_end()
         clocks = sampler.stop() if sampler is not None else None
         ms = torch.tensor([e0.elapsed_time(e1), self.prob.collect_gram_ms()], dtype=torch.float64,
                           device=self.device)

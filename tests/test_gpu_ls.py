@@ -81,3 +81,52 @@ def test_dimension_mismatch_is_an_error_not_a_crash(require_gpu, cpp_ls):
     rowptr, col, vals, cols, b, x0, _ = synth.random_sparse_system(100, 20, 3, seed=1)
     with pytest.raises(cpp_ls.CppLsError):
         cpp_ls.cg_least_squares(rowptr, col, vals, cols, b[:-1], x0=x0)
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithm 3: same CG + stopping rule, GPU-native summation (K3, the config-2 fast path).
+# Tolerance: relative solution error <= 1e-6 against the reference-order result (north star 1e-4).
+# ------------------------------------------------------------------------------------------------
+def _rel(a, b):
+    a, b = np.asarray(a).reshape(-1), np.asarray(b).reshape(-1)
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("rows,cols,per", [(20000, 500, 9), (5000, 300, 40), (300, 40, 3)])
+def test_ls_native_matches_reference_order(require_gpu, cpp_ls, oracle, rows, cols, per):
+    rowptr, col, vals, cols, b, x0, _ = synth.random_sparse_system(rows, cols, per, seed=rows)
+    x, it, rr = cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, algorithm=3, x0=x0)
+    xo, ito, rro = oracle.cg_least_squares(rowptr, col, vals, cols, b, x0, thread_count=1)
+    assert it == ito
+    assert _rel(x, xo) < 1e-6 and abs(rr - rro) <= 1e-6 * max(rro, 1e-12) + 1e-12
+
+
+def test_ls_native_bias_model(require_gpu, cpp_ls, oracle):
+    nu, ni, nnz = 3000, 1200, 200000
+    u, i = synth.rating_pairs(nu, ni, nnz, 3, 3, seed=21)
+    raw = synth.planted_ratings(u, i, nu, ni, seed=21, subtract_median=False)
+    rowptr, col, vals, cols, b, x0 = synth.bias_model_system(u, i, raw, nu, ni, seed=21)
+    x, it, rr = cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, algorithm=3, x0=x0)
+    xo, ito, rro = oracle.cg_least_squares(rowptr, col, vals, cols, b, x0, thread_count=8)
+    assert rr < 1e-6 and abs(it - ito) <= 1
+    x = x.reshape(-1)
+    pred, predo = x[u] + x[nu + i], xo[u] + xo[nu + i]
+    assert np.max(np.abs(pred - predo)) < 1e-5      # both converged to the rr < 1e-6 rule
+    info = cpp_ls.cg_least_squares.last_info
+    assert info.iterations == it and info.solve_ms > 0
+
+
+def test_ls_native_ragged_empty_and_termination(require_gpu, cpp_ls, oracle):
+    rng = np.random.default_rng(8)
+    rows, cols = 3000, 90
+    deg = rng.integers(0, 12, size=rows)
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    col = rng.integers(0, cols - 10, size=int(rowptr[-1])).astype(np.int32)
+    vals = rng.standard_normal(len(col))
+    b = rng.standard_normal(rows)
+    x0 = rng.uniform(-1, 1, cols)
+    for mrd, maxit in [(0.01, 200), (0.01, 3), (-1e300, 25), (0.01, 0)]:
+        x, it, rr = cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, mrd, maxit, algorithm=3, x0=x0)
+        xo, ito, rro = oracle.cg_least_squares(rowptr, col, vals, cols, b, x0, mrd, maxit, thread_count=1)
+        assert it == ito and _rel(x, xo) < 1e-6, (mrd, maxit)
+        assert bits_equal(x.reshape(-1)[-10:], x0[-10:])      # empty columns keep x0
