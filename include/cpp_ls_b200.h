@@ -177,6 +177,23 @@ MRB_API int mrb_als_collect_gram_ms(mrb_als_problem* p, float* out);
 /* Kernels launched by this library in this process so far. */
 MRB_API long long mrb_kernel_launches(void);
 
+/* ------------------------------------------------------------------------------------------
+ * 6. Extensions: movie-movie cosine similarity over the item factors with per-row top-k
+ *    (config 4).  The reference has no factor-based similarity (its SimilarMovieFinder,
+ *    python/full_data/build_similar_movies_db.py:21-221, works on co-rating vectors), so the
+ *    arithmetic is defined by oracle/ls_oracle.c:oracle_cosine_topk and met bit-exactly:
+ *    row-normalised fp64 factors, sequential sums, top-k by (score desc, id asc), self excluded.
+ *    Queries q_lo..q_hi-1 only: the multi-GPU split is by query block.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mrb_sim_info {
+    float candidates_ms;   /* normalisation + tensor-core GEMM fused with candidate selection */
+    float total_ms;        /* + exact re-score and final ordering (CUDA events) */
+    int fallback_rows;     /* queries recomputed exhaustively because the certificate failed */
+} mrb_sim_info;
+MRB_API int mrb_cosine_topk(const double* factors, int num_items, int num_factors, int topk,
+                            int q_lo, int q_hi, int* ids_out, double* scores_out,
+                            mrb_sim_info* info);
+
 #ifdef __cplusplus
 }
 #endif

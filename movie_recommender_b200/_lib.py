@@ -30,6 +30,12 @@ class LsInfo(ctypes.Structure):
                 ("transpose_ms", ctypes.c_float), ("solve_ms", ctypes.c_float)]
 
 
+class SimInfo(ctypes.Structure):
+    """mrb_sim_info (include/cpp_ls_b200.h)."""
+    _fields_ = [("candidates_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
+                ("fallback_rows", ctypes.c_int)]
+
+
 class CppLsError(RuntimeError):
     def __init__(self, code, message):
         super().__init__("cpp_ls_lib error %d: %s" % (code, message))
@@ -97,6 +103,9 @@ def _declare(dll):
     dll.mrb_als_shard_sse.argtypes = [c_void_p, c_void_p, _D]
     dll.mrb_als_collect_gram_ms.restype = c_int
     dll.mrb_als_collect_gram_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
+    dll.mrb_cosine_topk.restype = c_int
+    dll.mrb_cosine_topk.argtypes = [_D, c_int, c_int, c_int, c_int, c_int, _I, _D,
+                                    ctypes.POINTER(SimInfo)]
     dll.mrb_kernel_launches.restype = ctypes.c_longlong
     dll.mrb_kernel_launches.argtypes = []
     return dll

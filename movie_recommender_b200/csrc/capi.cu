@@ -9,6 +9,7 @@
 #include "faithful_cg.cuh"
 #include "index_build.cuh"
 #include "ls_native.cuh"
+#include "similarity.cuh"
 
 namespace mrb {
 static thread_local std::string g_last_error;
@@ -388,5 +389,21 @@ int mrb_als_collect_gram_ms(mrb_als_problem* p, float* out) {
 }
 
 long long mrb_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int mrb_cosine_topk(const double* factors, int num_items, int num_factors, int topk, int q_lo,
+                    int q_hi, int* ids_out, double* scores_out, mrb_sim_info* info) {
+    return guarded([&] {
+        MRB_REQUIRE(factors != nullptr && ids_out != nullptr && scores_out != nullptr,
+                    "mrb_cosine_topk: null argument");
+        SimResult r = cosine_topk(factors, num_items, num_factors, topk, q_lo, q_hi, ids_out,
+                                  scores_out);
+        if (info) {
+            info->candidates_ms = r.candidates_ms;
+            info->total_ms = r.total_ms;
+            info->fallback_rows = r.fallback_rows;
+        }
+        return 0;
+    });
+}
 
 }  // extern "C"

@@ -145,6 +145,26 @@ def rmse(user_ids, item_ids, ratings, k, user_factors, item_factors):
     return float(np.sqrt(np.mean(d * d))) if len(d) else 0.0
 
 
+def cosine_topk(M, topk, q_lo=0, q_hi=None):
+    """Factor-cosine top-k (PARITY UNPINNED: no reference counterpart, see ls_oracle.c).
+    Returns (ids[q, topk] int32 (-1 padded), scores[q, topk] float64) for queries q_lo..q_hi-1."""
+    M = _f64(M)
+    n, k = M.shape
+    q_hi = n if q_hi is None else q_hi
+    ids = np.zeros((q_hi - q_lo, topk), dtype=np.int32)
+    scores = np.zeros((q_hi - q_lo, topk), dtype=np.float64)
+    lib().oracle_cosine_topk(_dp(M), ctypes.c_int(n), ctypes.c_int(k), ctypes.c_int(topk),
+                             ctypes.c_int(q_lo), ctypes.c_int(q_hi), _ip(ids), _dp(scores))
+    return ids, scores
+
+
+def normalize_rows(M):
+    M = _f64(M)
+    out = np.zeros_like(M)
+    lib().oracle_normalize_rows(_dp(M), ctypes.c_int(M.shape[0]), ctypes.c_int(M.shape[1]), _dp(out))
+    return out
+
+
 # ----------------------------------------------------------------------- the real reference
 _ref = None
 
