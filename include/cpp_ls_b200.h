@@ -84,6 +84,9 @@ MRB_API int als_from_python(int* user_ids, int* item_ids, int ratings_length, do
 MRB_API const char* mrb_last_error(void);   /* message of the last failing call on this thread */
 MRB_API int mrb_device_count(void);         /* number of visible CUDA devices (0 if none / no driver) */
 MRB_API const char* mrb_build_info(void);   /* "sm_100a ..." */
+/* The library keeps freed device buffers in per-size free lists (repeated calls with the same
+ * shapes allocate nothing; MRB_NO_CACHE=1 disables it).  This returns them to the driver. */
+MRB_API void mrb_trim_memory(void);
 
 /* The generic sparse solver with a selectable algorithm: 1, 2 = the reference's two variants
  * (bit-faithful, same as the drop-in symbols above); 3 = the same CG and stopping rule with

@@ -106,6 +106,8 @@ def _declare(dll):
     dll.mrb_cosine_topk.restype = c_int
     dll.mrb_cosine_topk.argtypes = [_D, c_int, c_int, c_int, c_int, c_int, _I, _D,
                                     ctypes.POINTER(SimInfo)]
+    dll.mrb_trim_memory.restype = None
+    dll.mrb_trim_memory.argtypes = []
     dll.mrb_kernel_launches.restype = ctypes.c_longlong
     dll.mrb_kernel_launches.argtypes = []
     return dll

@@ -93,6 +93,29 @@ def cg_least_squares(A_row_indices: numpy.ndarray, A_col_indices: numpy.ndarray,
     return x, iterations, final_rr.value
 
 
+def _own_or_copy(a):
+    """Initial factors passed by the caller: a writable, contiguous float64 array flagged with
+    ``.flags.writeable`` AND marked ``inplace`` (see ``inplace_factors``) is updated in place
+    (keeps page-locked buffers page-locked across resumed calls); anything else is copied, so
+    the caller's array is never modified behind their back."""
+    if isinstance(a, _InPlace):
+        return a.array
+    return numpy.array(a, dtype=numpy.double).reshape(-1)
+
+
+class _InPlace:
+    def __init__(self, array):
+        if not (isinstance(array, numpy.ndarray) and array.dtype == numpy.double
+                and array.flags.c_contiguous and array.flags.writeable and array.ndim == 1):
+            raise ValueError("inplace_factors needs a writable contiguous 1-D float64 array")
+        self.array = array
+
+
+def inplace_factors(array):
+    """Wrap an initial-factor array to let ``als`` update it in place instead of copying it."""
+    return _InPlace(array)
+
+
 def als(user_ids: numpy.ndarray, item_ids: numpy.ndarray, ratings: numpy.ndarray,
         num_item_factors: int, num_users: int, num_items: int, min_r_decrease=0.01,
         max_iterations=200, algorithm=1, *, user_factors=None, item_factors=None):
@@ -110,11 +133,11 @@ def als(user_ids: numpy.ndarray, item_ids: numpy.ndarray, ratings: numpy.ndarray
     if user_factors is None:
         user_factors = numpy.random.uniform(-1, 1, num_users * num_user_factors)
     else:
-        user_factors = numpy.array(user_factors, dtype=numpy.double).reshape(-1)
+        user_factors = _own_or_copy(user_factors)
     if item_factors is None:
         item_factors = numpy.random.uniform(-1, 1, num_items * num_item_factors)
     else:
-        item_factors = numpy.array(item_factors, dtype=numpy.double).reshape(-1)
+        item_factors = _own_or_copy(item_factors)
     if len(user_factors) != num_users * num_user_factors or \
             len(item_factors) != num_items * num_item_factors:
         raise ValueError("initial factor arrays have the wrong length")

@@ -28,6 +28,9 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
     : nnz_(nnz), k_(k), nu_(num_users), ni_(num_items) {
     MRB_REQUIRE(nnz >= 0 && k >= 1 && num_users >= 0 && num_items >= 0, "als: bad sizes");
     MRB_CUDA(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
+    PhaseTimer t_all("AlsProblem ctor total");
+    {
+    PhaseTimer t_alloc("  alloc + upload + id check");
     user_ids_.alloc(nnz);
     item_ids_.alloc(nnz);
     ratings_.alloc(nnz);
@@ -54,6 +57,8 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
     MRB_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s_));
     MRB_CUDA(cudaStreamSynchronize(s_));
     MRB_REQUIRE(h_bad == 0, "als: user/item id outside [0, num_users/num_items)");
+    }
+    PhaseTimer t_idx("  index build (2 group_by)");
 
     cudaEvent_t e0, e1;
     MRB_CUDA(cudaEventCreate(&e0));

@@ -523,11 +523,16 @@ void build_side(Side& sd, const int* d_ptr, const int* d_idx, const int* d_other
     sd.lo = bounds[rank];
     sd.hi = bounds[rank + 1];
     // longest-processing-time-first order: owners by descending degree (stable)
+    // (counting sort by degree: stable, O(owners + max degree))
     std::vector<int> order(static_cast<size_t>(sd.hi - sd.lo));
-    std::iota(order.begin(), order.end(), sd.lo);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b];
-    });
+    {
+        int max_deg = 0;
+        for (int o = sd.lo; o < sd.hi; o++) max_deg = std::max(max_deg, ptr[o + 1] - ptr[o]);
+        std::vector<int> start(static_cast<size_t>(max_deg) + 2, 0);
+        for (int o = sd.lo; o < sd.hi; o++) start[max_deg - (ptr[o + 1] - ptr[o]) + 1]++;
+        for (int d = 0; d <= max_deg; d++) start[d + 1] += start[d];
+        for (int o = sd.lo; o < sd.hi; o++) order[start[max_deg - (ptr[o + 1] - ptr[o])]++] = o;
+    }
     std::vector<WorkItem> work;
     work.reserve(order.size() + nnz / GRAM_SEG + 1);
     sd.n_multi = 0;
@@ -648,6 +653,7 @@ void AlsProblem::ensure_gram() {
     const int m8 = (n_u + 1 + 7) / 8;
     MRB_REQUIRE(m8 <= 7, "als algorithm 3/4: rank above 54 is not supported yet");
     if (gram_ && gram_->built_rank == rank_ && gram_->built_world == world_) return;
+    PhaseTimer t_g("ensure_gram (work lists)");
     gram_ = std::make_shared<GramState>();
     GramState& g = *gram_;
     int dev = 0;

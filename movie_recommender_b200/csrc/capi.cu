@@ -102,10 +102,19 @@ int als_from_python(int* user_ids, int* item_ids, int ratings_length, double* ra
                     "als: len(user_factors) is not a multiple of num_item_factors + 1");
         MRB_REQUIRE(item_factors_length % k == 0,
                     "als: len(item_factors) is not a multiple of num_item_factors");
+        PhaseTimer t_all("als_from_python total");
         AlsProblem p(user_ids, item_ids, ratings_length, ratings_values, k,
                      user_factors_length / (k + 1), item_factors_length / k);
-        p.set_factors(user_factors_values, item_factors_values);
-        AlsRunInfo info = p.run(algorithm, min_r_decrease, max_iteration, g_thread_count);
+        {
+            PhaseTimer t("set_factors");
+            p.set_factors(user_factors_values, item_factors_values);
+        }
+        AlsRunInfo info;
+        {
+            PhaseTimer t("run");
+            info = p.run(algorithm, min_r_decrease, max_iteration, g_thread_count);
+        }
+        PhaseTimer t("get_factors + teardown");
         p.get_factors(user_factors_values, item_factors_values);
         return info.sweeps_returned;
     });
@@ -389,6 +398,8 @@ int mrb_als_collect_gram_ms(mrb_als_problem* p, float* out) {
 }
 
 long long mrb_kernel_launches(void) { return g_kernel_launches.load(); }
+
+void mrb_trim_memory(void) { arena_trim(); }
 
 int mrb_cosine_topk(const double* factors, int num_items, int num_factors, int topk, int q_lo,
                     int q_hi, int* ids_out, double* scores_out, mrb_sim_info* info) {

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -43,6 +45,17 @@ void set_last_error(const std::string& msg);
         if (!(cond)) throw ::mrb::Error(::mrb::kErrArgument, (msg));  \
     } while (0)
 
+// Device memory arena.  cudaMalloc / cudaFree of the multi-hundred-MB buffers of one als() call
+// cost tens to hundreds of milliseconds on this platform (and cudaFree synchronises the device),
+// which dominated the end-to-end time of the drop-in call.  Freed blocks are therefore kept in
+// per-size free lists and handed out again; a repeated call with the same shapes allocates
+// nothing.  Safe because every library entry point synchronises its stream before its buffers
+// die (and a buffer released during exception unwinding synchronises the device first).
+// MRB_NO_CACHE=1 disables the cache; mrb_trim_memory() returns everything to the driver.
+void* arena_alloc(size_t bytes);
+void arena_free(void* p);
+void arena_trim();
+
 // RAII device allocation.
 template <typename T>
 struct DevBuf {
@@ -61,10 +74,10 @@ struct DevBuf {
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) MRB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+        if (count) p = static_cast<T*>(arena_alloc(count * sizeof(T)));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) arena_free(p);
         p = nullptr;
         n = 0;
     }
@@ -89,6 +102,23 @@ struct PinnedBuf {
 // Number of kernels this library has launched (what bench.py reports as gpu_launches).
 inline std::atomic<long long> g_kernel_launches{0};
 #define MRB_LAUNCHED(n) (::mrb::g_kernel_launches.fetch_add((n), std::memory_order_relaxed))
+
+// Host-side phase timer, printed to stderr when MRB_TIMING is set (development aid).
+struct PhaseTimer {
+    const char* what;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    explicit PhaseTimer(const char* w) : what(w), t0(std::chrono::steady_clock::now()),
+                                         on(std::getenv("MRB_TIMING") != nullptr) {}
+    ~PhaseTimer() {
+        if (on) {
+            cudaDeviceSynchronize();
+            const double ms = std::chrono::duration<double, std::milli>(
+                                  std::chrono::steady_clock::now() - t0).count();
+            std::fprintf(stderr, "[mrb timing] %-28s %8.2f ms\n", what, ms);
+        }
+    }
+};
 
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
