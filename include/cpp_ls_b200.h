@@ -197,6 +197,26 @@ MRB_API int mrb_cosine_topk(const double* factors, int num_items, int num_factor
                             int q_lo, int q_hi, int* ids_out, double* scores_out,
                             mrb_sim_info* info);
 
+/* ------------------------------------------------------------------------------------------
+ * 7. Extensions: the reference's co-rating similarity, SimilarMovieFinder
+ *    (python/full_data/build_similar_movies_db.py:21-221: genre gate :44-69, cosine over the
+ *    common raters with the log "buff" :72-119, reliability cut and top-k :151-180), bit-exact.
+ *    Inputs are two CSR views of the same ratings (by movie list index and by user), ratings as
+ *    rq = 2*rating (0.5 grid, rq <= 20), a genre bit mask and genre count per movie (count 0 =
+ *    no genre entry), and buff[n] tabulated by the host with the reference's libm calls.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mrb_cosim mrb_cosim;
+MRB_API int mrb_cosim_create(int num_movies, int num_users, const int* m_ptr, const int* m_user,
+                             const unsigned char* m_rq, const int* u_ptr, const int* u_movie,
+                             const unsigned char* u_rq, const unsigned long long* genre_mask,
+                             const int* genre_cnt, mrb_cosim** out);
+/* Queries q_lo..q_hi-1: out_idx / out_score are (q_hi-q_lo) x num_results (list indices, -1
+ * padded), out_count the number of results per query; num_results <= 56. */
+MRB_API int mrb_cosim_query(mrb_cosim* h, int q_lo, int q_hi, const double* buff, int buff_len,
+                            int num_results, int* out_idx, double* out_score, int* out_count,
+                            float* kernel_ms);
+MRB_API void mrb_cosim_destroy(mrb_cosim* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,6 +106,16 @@ def _declare(dll):
     dll.mrb_cosine_topk.restype = c_int
     dll.mrb_cosine_topk.argtypes = [_D, c_int, c_int, c_int, c_int, c_int, _I, _D,
                                     ctypes.POINTER(SimInfo)]
+    _UB = ctypes.POINTER(ctypes.c_ubyte)
+    _U64 = ctypes.POINTER(ctypes.c_ulonglong)
+    dll.mrb_cosim_create.restype = c_int
+    dll.mrb_cosim_create.argtypes = [c_int, c_int, _I, _I, _UB, _I, _I, _UB, _U64, _I,
+                                     ctypes.POINTER(c_void_p)]
+    dll.mrb_cosim_query.restype = c_int
+    dll.mrb_cosim_query.argtypes = [c_void_p, c_int, c_int, _D, c_int, c_int, _I, _D, _I,
+                                    ctypes.POINTER(ctypes.c_float)]
+    dll.mrb_cosim_destroy.restype = None
+    dll.mrb_cosim_destroy.argtypes = [c_void_p]
     dll.mrb_trim_memory.restype = None
     dll.mrb_trim_memory.argtypes = []
     dll.mrb_kernel_launches.restype = ctypes.c_longlong

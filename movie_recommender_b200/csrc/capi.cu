@@ -10,6 +10,7 @@
 #include "index_build.cuh"
 #include "ls_native.cuh"
 #include "similarity.cuh"
+#include "cosim.cuh"
 
 namespace mrb {
 static thread_local std::string g_last_error;
@@ -400,6 +401,39 @@ int mrb_als_collect_gram_ms(mrb_als_problem* p, float* out) {
 long long mrb_kernel_launches(void) { return g_kernel_launches.load(); }
 
 void mrb_trim_memory(void) { arena_trim(); }
+
+struct mrb_cosim {
+    Cosim impl;
+    mrb_cosim(int nm, int nu, const int* mp, const int* mu, const unsigned char* mr, const int* up,
+              const int* um, const unsigned char* ur, const unsigned long long* gm, const int* gc)
+        : impl(nm, nu, mp, mu, mr, up, um, ur, gm, gc) {}
+};
+
+int mrb_cosim_create(int num_movies, int num_users, const int* m_ptr, const int* m_user,
+                     const unsigned char* m_rq, const int* u_ptr, const int* u_movie,
+                     const unsigned char* u_rq, const unsigned long long* genre_mask,
+                     const int* genre_cnt, mrb_cosim** out) {
+    return guarded([&] {
+        MRB_REQUIRE(out != nullptr, "mrb_cosim_create: null out");
+        *out = new mrb_cosim(num_movies, num_users, m_ptr, m_user, m_rq, u_ptr, u_movie, u_rq,
+                             genre_mask, genre_cnt);
+        return 0;
+    });
+}
+
+int mrb_cosim_query(mrb_cosim* h, int q_lo, int q_hi, const double* buff, int buff_len,
+                    int num_results, int* out_idx, double* out_score, int* out_count,
+                    float* kernel_ms) {
+    return guarded([&] {
+        MRB_REQUIRE(h != nullptr, "null handle");
+        const float ms = h->impl.query(q_lo, q_hi, buff, buff_len, num_results, out_idx, out_score,
+                                       out_count);
+        if (kernel_ms) *kernel_ms = ms;
+        return 0;
+    });
+}
+
+void mrb_cosim_destroy(mrb_cosim* h) { delete h; }
 
 int mrb_cosine_topk(const double* factors, int num_items, int num_factors, int topk, int q_lo,
                     int q_hi, int* ids_out, double* scores_out, mrb_sim_info* info) {

@@ -1,0 +1,34 @@
+// K6: the reference's co-rating similarity (SimilarMovieFinder) on the GPU (see cosim.cu).
+#pragma once
+#include "common.cuh"
+
+namespace mrb {
+
+class Cosim {
+public:
+    // Host CSR views of the same ratings: by movie (raters) and by user (movies); rq = 2*rating
+    // (ratings on the 0.5 grid, 0 <= rq <= 20); genre bit masks and genre counts per movie
+    // (count 0 = the movie has no genre entry).
+    Cosim(int num_movies, int num_users, const int* m_ptr, const int* m_user,
+          const unsigned char* m_rq, const int* u_ptr, const int* u_movie,
+          const unsigned char* u_rq, const unsigned long long* genre_mask, const int* genre_cnt);
+    ~Cosim();
+    Cosim(const Cosim&) = delete;
+    Cosim& operator=(const Cosim&) = delete;
+
+    // Queries q_lo..q_hi-1 (movie list indices).  buff[n] = score boost for n common raters.
+    // Outputs (q_hi-q_lo) x num_results list indices (-1 padded) and scores, and the number of
+    // results per query.  Returns the CUDA-event time of the kernel in ms.
+    float query(int q_lo, int q_hi, const double* buff, int buff_len, int num_results,
+                int* out_idx, double* out_score, int* out_count);
+
+private:
+    int N_, U_, ctas_ = 0;
+    cudaStream_t s_ = nullptr;
+    DevBuf<int> m_ptr_, m_user_, u_ptr_, u_movie_, gcnt_, cand_b_, cand_n_, counter_;
+    DevBuf<unsigned char> m_rq_, u_rq_;
+    DevBuf<unsigned long long> gmask_, scratch_;
+    DevBuf<double> cand_s_;
+};
+
+}  // namespace mrb

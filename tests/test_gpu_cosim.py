@@ -1,0 +1,74 @@
+"""K6: the reference's co-rating similarity (SimilarMovieFinder) on the GPU, through the Python
+mirror of the reference class.  ids equal and scores BIT-equal to the REAL reference class
+(golden results in tests/golden/similar_*.json) and to the oracle on further catalogues,
+including the reliability cut, movies without genres, and tune()."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle.similar_oracle import SimilarOracle, synthetic_catalogue
+
+pytestmark = pytest.mark.gpu
+
+
+def finder_cls():
+    from movie_recommender_b200.build_similar_movies_db import SimilarMovieFinder
+    return SimilarMovieFinder
+
+
+def load(name):
+    with open(os.path.join(GOLDEN, "similar_%s.json" % name)) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("name", ["small", "dense", "cut"])
+def test_matches_the_real_reference_class(require_gpu, name):
+    g = load(name)
+    genres, ratings = synthetic_catalogue(**g["params"])
+    f = finder_cls()(genres, ratings)
+    for key, nres in (("results", 20), ("results_top3", 3)):
+        for i_str, (ids, hexscores) in g[key].items():
+            gi, gs = f.find_similar_movie(int(i_str), num_results=nres)
+            assert list(gi) == ids, (key, i_str)
+            assert [float(s).hex() for s in gs] == hexscores, (key, i_str)
+    if "tune" in g:
+        t = g["tune"]
+        f.tune(t["movie_id1"], t["movie_id2"], 2, 20)
+        assert f.buff_point == t["buff_point"] and float(f.buff_limit).hex() == t["buff_limit"]
+        gi, gs = f.find_similar_movie(f.find_movie_index(t["movie_id1"]))
+        assert list(gi) == t["after"][0] and [float(s).hex() for s in gs] == t["after"][1]
+    f.close()
+
+
+def test_build_equals_per_movie_queries_and_oracle(require_gpu):
+    genres, ratings = synthetic_catalogue(num_movies=300, num_users=400, density=0.5, seed=11)
+    f = finder_cls()(genres, ratings, buff_limit=0.2, buff_point=40)
+    o = SimilarOracle(genres, ratings, buff_limit=0.2, buff_point=40)
+    db = f.build()
+    parts = {}
+    parts.update(f.build(start=0, length=100))          # the multi-GPU split is by query range
+    parts.update(f.build(start=100, length=200))
+    assert parts == db
+    for i, (mid, _) in enumerate(ratings):
+        oi, os_ = o.find_similar_movie(i)
+        assert tuple(db.get(mid, ())) == tuple(oi)
+        gi, gs = f.find_similar_movie(i)
+        assert [float(s).hex() for s in gs] == [float(s).hex() for s in os_]
+    f.close()
+
+
+def test_edge_cases(require_gpu):
+    F = finder_cls()
+    # nobody shares three raters: no results at all
+    ratings = [(1, {10: 4.0, 11: 3.5}), (2, {10: 2.0, 12: 5.0}), (3, {13: 1.0})]
+    genres = {1: {0}, 2: {0}, 3: {0}}
+    f = F(genres, ratings)
+    assert f.find_similar_movie(0) == ([], []) and f.build() == {}
+    assert f.find_movie_index(3) == 2 and f.find_movie_index(99) == -1
+    f.close()
+    # off-grid ratings are refused (the kernel's exact integer accumulation needs the 0.5 grid)
+    with pytest.raises(ValueError):
+        F({1: {0}}, [(1, {10: 3.3})])
