@@ -40,7 +40,24 @@ class SimilarMovieFinder:
         self.buff_limit = buff_limit
         self.buff_point = buff_point
         self._h = ctypes.c_void_p()
-        self._upload()
+        if movie_ratings is not None:
+            self._upload()
+
+    @classmethod
+    def from_arrays(cls, movie_genres, movie_ids, movie_index_of_rating, user_ids, ratings,
+                    buff_limit=0.05, buff_point=100):
+        """Array form of the same input (extension): ``movie_ids[i]`` is the id of list entry i;
+        rating j belongs to list entry ``movie_index_of_rating[j]`` (non-decreasing), user
+        ``user_ids[j]``.  Avoids building 27 M-entry Python dicts for catalogue-scale runs;
+        ``tune`` needs the dict form."""
+        self = cls(movie_genres, None, buff_limit, buff_point)
+        self._movie_ids = numpy.asarray(movie_ids, dtype=numpy.int64)
+        movie_of = numpy.ascontiguousarray(movie_index_of_rating, dtype=numpy.int32)
+        if len(movie_of) and numpy.any(numpy.diff(movie_of) < 0):
+            raise ValueError("ratings must be grouped by movie list index")
+        self._from_arrays(len(self._movie_ids), movie_of, numpy.asarray(user_ids, dtype=numpy.int64),
+                          numpy.asarray(ratings, dtype=numpy.float64))
+        return self
 
     # ------------------------------------------------------------------ host-side marshalling
     def _upload(self):
