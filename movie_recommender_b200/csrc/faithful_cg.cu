@@ -42,12 +42,21 @@ k_dot_partials(const double* __restrict__ a, const double* __restrict__ b,
     for (int t = 0; t < ntiles; t++) {
         if (t + 1 < ntiles) fill(t + 1, (t + 1) & 1);
         if (tid == 0) {
+            // the dependent-add chain; the next 8 addends are fetched from shared memory while
+            // the current 8 are being added, so only the add latency is on the critical path
             const int cnt = min(DOT_TILE, len - t * DOT_TILE);
             const double* src = buf[t & 1];
             int i = 0;
-            for (; i + 8 <= cnt; i += 8) {
-                const double v0 = src[i], v1 = src[i + 1], v2 = src[i + 2], v3 = src[i + 3];
-                const double v4 = src[i + 4], v5 = src[i + 5], v6 = src[i + 6], v7 = src[i + 7];
+            if (cnt >= 8) {
+                double v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
+                double v4 = src[4], v5 = src[5], v6 = src[6], v7 = src[7];
+                for (i = 8; i + 8 <= cnt; i += 8) {
+                    const double w0 = src[i], w1 = src[i + 1], w2 = src[i + 2], w3 = src[i + 3];
+                    const double w4 = src[i + 4], w5 = src[i + 5], w6 = src[i + 6], w7 = src[i + 7];
+                    s = xadd(s, v0); s = xadd(s, v1); s = xadd(s, v2); s = xadd(s, v3);
+                    s = xadd(s, v4); s = xadd(s, v5); s = xadd(s, v6); s = xadd(s, v7);
+                    v0 = w0; v1 = w1; v2 = w2; v3 = w3; v4 = w4; v5 = w5; v6 = w6; v7 = w7;
+                }
                 s = xadd(s, v0); s = xadd(s, v1); s = xadd(s, v2); s = xadd(s, v3);
                 s = xadd(s, v4); s = xadd(s, v5); s = xadd(s, v6); s = xadd(s, v7);
             }
