@@ -194,32 +194,38 @@ __device__ __forceinline__ void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], 
 #pragma unroll
     for (int tk = 0; tk < M8; tk++) {
         const int D = TI(tk, tk);
+        // the 8 pivot columns, rolled in pairs (cp = c >> 1 at run time, slot j = c & 1 static):
+        // 4x less code than a full unroll -- the epilogue was instruction-cache bound
+#pragma unroll 1
+        for (int cp = 0; cp < 4; cp++) {
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            if (8 * tk + c < n) {   // warp-uniform: only the last tile column has non-pivot columns
-                const int src_cc = c * 4 + (c >> 1);
-                const double d = shfl_double(acc[D][c & 1], src_cc);
-                const double th = shfl_double(thr[tk], src_cc);
-                const bool ok = d > th && th > 0.0;   // false for NaN
-                const double inv = ok ? rsqrt(d) : 0.0;
-                if (p == c) invd[tk] = inv;
-                if (q == (c >> 1)) {
-                    const double v = acc[D][c & 1];
-                    if (p >= c) acc[D][c & 1] = ok ? v * inv : 0.0;   // p == c: d * rsqrt(d) = sqrt(d)
+            for (int j = 0; j < 2; j++) {
+                const int c = 2 * cp + j;
+                if (8 * tk + c < n) {   // warp-uniform: only the last tile column has non-pivot columns
+                    const int src_cc = c * 4 + cp;
+                    const double d = shfl_double(acc[D][j], src_cc);
+                    const double th = shfl_double(thr[tk], src_cc);
+                    const bool ok = d > th && th > 0.0;   // false for NaN
+                    const double inv = ok ? rsqrt(d) : 0.0;
+                    if (p == c) invd[tk] = inv;
+                    if (q == cp) {
+                        const double v = acc[D][j];
+                        if (p >= c) acc[D][j] = ok ? v * inv : 0.0;   // p == c: d * rsqrt(d) = sqrt(d)
 #pragma unroll
-                    for (int ti = tk + 1; ti < M8; ti++)
-                        acc[TI(ti, tk)][c & 1] = ok ? acc[TI(ti, tk)][c & 1] * inv : 0.0;
-                }
-                if (c < 7) {
-                    // D[c2][c] for this lane's two columns c2 = 2q, 2q+1
-                    const double dc20 = shfl_double(acc[D][c & 1], (2 * q) * 4 + (c >> 1));
-                    const double dc21 = shfl_double(acc[D][c & 1], (2 * q + 1) * 4 + (c >> 1));
+                        for (int ti = tk + 1; ti < M8; ti++)
+                            acc[TI(ti, tk)][j] = ok ? acc[TI(ti, tk)][j] * inv : 0.0;
+                    }
+                    if (c < 7) {
+                        // D[c2][c] for this lane's two columns c2 = 2q, 2q+1
+                        const double dc20 = shfl_double(acc[D][j], (2 * q) * 4 + cp);
+                        const double dc21 = shfl_double(acc[D][j], (2 * q + 1) * 4 + cp);
 #pragma unroll
-                    for (int ti = tk; ti < M8; ti++) {
-                        const int X = TI(ti, tk);
-                        const double xrc = shfl_double(acc[X][c & 1], p * 4 + (c >> 1));   // X[p][c]
-                        if (2 * q > c) acc[X][0] -= xrc * dc20;
-                        if (2 * q + 1 > c) acc[X][1] -= xrc * dc21;
+                        for (int ti = tk; ti < M8; ti++) {
+                            const int X = TI(ti, tk);
+                            const double xrc = shfl_double(acc[X][j], p * 4 + cp);   // X[p][c]
+                            if (2 * q > c) acc[X][0] -= xrc * dc20;
+                            if (2 * q + 1 > c) acc[X][1] -= xrc * dc21;
+                        }
                     }
                 }
             }
@@ -264,18 +270,22 @@ __device__ __forceinline__ void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], 
 #pragma unroll
     for (int tj = M8 - 1; tj >= 0; tj--) {
         const int D = TI(tj, tj);
+#pragma unroll 1
+        for (int cp = 3; cp >= 0; cp--) {
 #pragma unroll
-        for (int c = 7; c >= 0; c--) {
-            if (8 * tj + c < n) {
-                const double yc = shfl_double(y[tj][c & 1], c >> 1);
-                const double inv = shfl_double(invd[tj], c * 4);
-                const double dc = yc * inv;
-                if (q == (c >> 1)) dl[tj][c & 1] = dc;
-                if (c > 0) {
-                    const double l0 = shfl_double(acc[D][0], c * 4 + q);   // L[c][2q]
-                    const double l1 = shfl_double(acc[D][1], c * 4 + q);   // L[c][2q+1]
-                    if (2 * q < c) y[tj][0] -= l0 * dc;
-                    if (2 * q + 1 < c) y[tj][1] -= l1 * dc;
+            for (int j = 1; j >= 0; j--) {
+                const int c = 2 * cp + j;
+                if (8 * tj + c < n) {
+                    const double yc = shfl_double(y[tj][j], cp);
+                    const double inv = shfl_double(invd[tj], c * 4);
+                    const double dc = yc * inv;
+                    if (q == cp) dl[tj][j] = dc;
+                    if (c > 0) {
+                        const double l0 = shfl_double(acc[D][0], c * 4 + q);   // L[c][2q]
+                        const double l1 = shfl_double(acc[D][1], c * 4 + q);   // L[c][2q+1]
+                        if (2 * q < c) y[tj][0] -= l0 * dc;
+                        if (2 * q + 1 < c) y[tj][1] -= l1 * dc;
+                    }
                 }
             }
         }
