@@ -487,16 +487,20 @@ __global__ void k_gather_grouped(const int* __restrict__ idx, const int* __restr
 
 }  // namespace
 
-// bounds[r] = first owner of rank r: contiguous ranges holding ~nnz/world ratings each.
+// bounds[r] = first owner of rank r: contiguous ranges of equal COST, where a row costs its
+// ratings plus a constant for its solve (measured at rank 50: the Cholesky epilogue of one row
+// takes as long as accumulating ~100 ratings, profiles/ncu_k_gram_C3_r01_v3.txt).
 void balanced_ranges(const int* ptr, int owners, int world, int* bounds) {
-    const long long nnz = ptr[owners];
+    constexpr long long kRowCost = 100;
+    auto cost_before = [&](int o) { return static_cast<long long>(ptr[o]) + kRowCost * o; };
+    const long long total = cost_before(owners);
     bounds[0] = 0;
     int o = 0;
     for (int r = 1; r < world; r++) {
-        const long long target = nnz * r / world;
-        while (o < owners && ptr[o] < target) o++;
+        const long long target = total * r / world;
+        while (o < owners && cost_before(o) < target) o++;
         // the boundary nearest to the target (never before the previous boundary)
-        if (o > bounds[r - 1] && target - ptr[o - 1] < ptr[o] - target) o--;
+        if (o > bounds[r - 1] && target - cost_before(o - 1) < cost_before(o) - target) o--;
         bounds[r] = o;
     }
     bounds[world] = owners;

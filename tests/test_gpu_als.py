@@ -64,7 +64,7 @@ def test_als_rank50_bitexact(require_gpu, cpp_ls, oracle):
     assert it == ito and bits_equal(uf, uo) and bits_equal(itf, io)
 
 
-@pytest.mark.parametrize("k", [1, 31, 32, 33, 70])
+@pytest.mark.parametrize("k", [1, 31, 32, 33, 70, 128])
 def test_als_rank_edges_bitexact(require_gpu, cpp_ls, oracle, k):
     p = synth.als_problem(90, 160, 9000, k, seed=k, min_degrees=False)
     cpp_ls.set_thread_count(3)

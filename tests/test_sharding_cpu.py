@@ -29,10 +29,12 @@ dist.all_gather_object(allr, mine)
 assert allr[0][0] == 0 and allr[-1][1] == 3000 and allr[0][2] == 0 and allr[-1][3] == 700
 for a, b in zip(allr[:-1], allr[1:]):
     assert a[1] == b[0] and a[3] == b[2]
-# every rank's share of the ratings is within 5 %% of nnz / world
+# every rank's share of the cost (ratings + 100 per row for its solve) is within 5 %% of the mean
 for r in allr:
-    assert abs((uptr[r[1]] - uptr[r[0]]) - 90000 / world) < 0.05 * 90000
-    assert abs((iptr[r[3]] - iptr[r[2]]) - 90000 / world) < 0.05 * 90000
+    cu = (uptr[r[1]] - uptr[r[0]]) + 100 * (r[1] - r[0])
+    ci = (iptr[r[3]] - iptr[r[2]]) + 100 * (r[3] - r[2])
+    assert abs(cu - (90000 + 100 * 3000) / world) < 0.05 * (90000 + 100 * 3000)
+    assert abs(ci - (90000 + 100 * 700) / world) < 0.05 * (90000 + 100 * 700)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok", mine)
