@@ -1,6 +1,7 @@
 // Reference-order conjugate gradient (see faithful_cg.cuh for the contract).
 #include "faithful_cg.cuh"
 
+#include <algorithm>
 #include <climits>
 
 #include "index_build.cuh"
@@ -212,45 +213,115 @@ __global__ void k_csr_mul(const int* __restrict__ rowptr, const int* __restrict_
     y[r] = s;
 }
 
-// One warp per column of A.  32 entries are fetched and multiplied in parallel; the running
-// sum is then advanced entry by entry (every lane carries the same chain), folding the partial
-// into the total whenever the row index crosses a reference chunk boundary.
+// chunk of row r: smallest c with r < bounds[c + 1]
+__device__ __forceinline__ int chunk_of(const int* __restrict__ bounds, int nchunks, int r) {
+    int lo = 0, hi = nchunks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (r < bounds[mid + 1]) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__global__ void k_seg_flags(const int* __restrict__ pos, int n, const int* __restrict__ bounds,
+                            int nchunks, int* __restrict__ flags) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > n) return;
+    if (e == n) { flags[n] = 0; return; }
+    const int c = chunk_of(bounds, nchunks, pos[e]);
+    const int cp = e > 0 ? chunk_of(bounds, nchunks, pos[e - 1]) : -1;
+    flags[e] = c != cp ? 1 : 0;
+}
+
+__global__ void k_seg_group_flags(const int* __restrict__ ptr, int ngroups, int* __restrict__ flags) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < ngroups && ptr[g] < ptr[g + 1]) flags[ptr[g]] = 1;
+}
+
+__global__ void k_seg_starts(const int* __restrict__ flags, const int* __restrict__ scan, int n,
+                             int* __restrict__ seg_start) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > n) return;
+    if (e == n) { seg_start[scan[n]] = n; return; }
+    if (flags[e]) seg_start[scan[e]] = e;
+}
+
+__global__ void k_grp_seg_ptr(const int* __restrict__ ptr, const int* __restrict__ scan,
+                              int ngroups, int* __restrict__ grp_seg_ptr) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g <= ngroups) grp_seg_ptr[g] = scan[ptr[g]];
+}
+
+// One warp per (column, chunk) segment: 32 entries are fetched and multiplied in parallel (the
+// next 32 are requested before the current ones are consumed), then added in entry order.
 __global__ void __launch_bounds__(256)
-k_csc_tmul(const int* __restrict__ t_ptr, const int* __restrict__ t_row,
-           const double* __restrict__ t_val, const double* __restrict__ t, double* __restrict__ y,
-           int cols, const int* __restrict__ bounds, const int* __restrict__ guard) {
+k_csc_seg_partial(const int* __restrict__ seg_start, int nseg, const int* __restrict__ t_row,
+                  const double* __restrict__ t_val, const double* __restrict__ t,
+                  double* __restrict__ partial, const int* __restrict__ guard) {
     if (guard && *guard) return;
-    const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (col >= cols) return;
+    const int sg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (sg >= nseg) return;
     const int lane = threadIdx.x & 31;
-    const int beg = t_ptr[col], end = t_ptr[col + 1];
-    double acc = 0, tot = 0;
-    int c = 0, next = bounds[1];
+    const int beg = seg_start[sg], end = seg_start[sg + 1];
+    double acc = 0;
+    double prod_next = 0;
+    if (beg + lane < end) prod_next = xmul(t[t_row[beg + lane]], t_val[beg + lane]);   // :244
     for (int e0 = beg; e0 < end; e0 += 32) {
-        const int e = e0 + lane;
-        int row_l = INT_MAX;
-        double prod_l = 0;
-        if (e < end) {
-            row_l = t_row[e];
-            prod_l = xmul(t[row_l], t_val[e]);  // matrix.cpp:244 (c_i * values[j])
-        }
+        const double prod_l = prod_next;
+        const int en = e0 + 32 + lane;
+        prod_next = 0;
+        if (en < end) prod_next = xmul(t[t_row[en]], t_val[en]);
         const int cnt = min(32, end - e0);
-        for (int i = 0; i < cnt; i++) {
-            const int row = __shfl_sync(0xffffffffu, row_l, i);
-            const double prod = shfl_double(prod_l, i);
-            if (row >= next) {  // next reference thread's private vector (matrix.cpp:426-448)
-                tot = xadd(tot, acc);
-                acc = 0;
-                while (row >= bounds[c + 1]) c++;
-                next = bounds[c + 1];
-            }
-            acc = xadd(acc, prod);
+        if (cnt == 32) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) acc = xadd(acc, shfl_double(prod_l, i));
+        } else {
+            for (int i = 0; i < cnt; i++) acc = xadd(acc, shfl_double(prod_l, i));
         }
     }
-    tot = xadd(tot, acc);
-    if (lane == 0) y[col] = tot;
+    if (lane == 0) partial[sg] = acc;
+}
+
+// Fold of the per-chunk sums in chunk order (add_merge, matrix.cpp:106-125); width values per
+// group, one thread per output.
+__global__ void __launch_bounds__(256)
+k_seg_fold(const int* __restrict__ grp_seg_ptr, const double* __restrict__ partial,
+           double* __restrict__ y, long long outputs, int width, const int* __restrict__ guard) {
+    if (guard && *guard) return;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= outputs) return;
+    const int g = static_cast<int>(i / width), j = static_cast<int>(i - static_cast<long long>(g) * width);
+    double tot = 0;
+    const int se = grp_seg_ptr[g + 1];
+    for (int sg = grp_seg_ptr[g]; sg < se; sg++)
+        tot = xadd(tot, partial[static_cast<size_t>(sg) * width + j]);
+    y[i] = tot;
 }
 }  // namespace
+
+void build_segments(SegTable& out, const int* d_grp_ptr, const int* d_pos, int ngroups, int n,
+                    const int* d_bounds, int nchunks, int width, cudaStream_t s) {
+    DevBuf<int> flags(static_cast<size_t>(n) + 1), scan(static_cast<size_t>(n) + 1);
+    k_seg_flags<<<ceil_div(n + 1ll, 256), 256, 0, s>>>(d_pos, n, d_bounds, nchunks, flags.p);
+    k_seg_group_flags<<<ceil_div(ngroups > 0 ? ngroups : 1, 256), 256, 0, s>>>(d_grp_ptr, ngroups, flags.p);
+    MRB_LAUNCHED(2);
+    MRB_CUDA(cudaGetLastError());
+    exclusive_scan_i32(flags.p, scan.p, static_cast<long long>(n) + 1, s);
+    int nseg = 0;
+    MRB_CUDA(cudaMemcpyAsync(&nseg, scan.p + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MRB_CUDA(cudaStreamSynchronize(s));
+    out.nseg = nseg;
+    out.seg_start.alloc(static_cast<size_t>(nseg) + 1);
+    out.grp_seg_ptr.alloc(static_cast<size_t>(ngroups) + 1);
+    out.partial.alloc(std::max<size_t>(static_cast<size_t>(nseg) * width, 1));
+    k_seg_starts<<<ceil_div(n + 1ll, 256), 256, 0, s>>>(flags.p, scan.p, n, out.seg_start.p);
+    k_grp_seg_ptr<<<ceil_div(ngroups + 1ll, 256), 256, 0, s>>>(d_grp_ptr, scan.p, ngroups, out.grp_seg_ptr.p);
+    MRB_LAUNCHED(2);
+    MRB_CUDA(cudaGetLastError());
+    MRB_CUDA(cudaStreamSynchronize(s));   // flags / scan die here
+    out.bounds_key = d_bounds;
+    out.nchunks_key = nchunks;
+}
 
 CsrFaithfulOp::CsrFaithfulOp(int rows_in, int cols_in, int nnz, const int* d_rowptr,
                              const int* d_colidx, const double* d_vals, cudaStream_t s)
@@ -266,11 +337,17 @@ void CsrFaithfulOp::mul(const double* d_x, double* d_y, cudaStream_t s) {
     k_csr_mul<<<ceil_div(rows, 256), 256, 0, s>>>(rowptr_, colidx_, vals_, d_x, d_y, rows, guard); MRB_LAUNCHED(1);
 }
 
-void CsrFaithfulOp::tmul(const double* d_t, double* d_y, const int* d_row_bounds, int /*nchunks*/,
+void CsrFaithfulOp::tmul(const double* d_t, double* d_y, const int* d_row_bounds, int nchunks,
                          cudaStream_t s) {
     if (cols == 0) return;
-    k_csc_tmul<<<ceil_div(static_cast<long long>(cols) * 32, 256), 256, 0, s>>>(
-        t_ptr_.p, t_row_.p, t_val_.p, d_t, d_y, cols, d_row_bounds, guard); MRB_LAUNCHED(1);
+    SegTable& st = seg_[nchunks == 1 ? 1 : 0];
+    if (st.bounds_key != d_row_bounds || st.nchunks_key != nchunks)
+        build_segments(st, t_ptr_.p, t_row_.p, cols, nnz_, d_row_bounds, nchunks, 1, s);
+    if (st.nseg > 0)
+        k_csc_seg_partial<<<ceil_div(static_cast<long long>(st.nseg) * 32, 256), 256, 0, s>>>(
+            st.seg_start.p, st.nseg, t_row_.p, t_val_.p, d_t, st.partial.p, guard);
+    k_seg_fold<<<ceil_div(cols, 256), 256, 0, s>>>(st.grp_seg_ptr.p, st.partial.p, d_y, cols, 1, guard);
+    MRB_LAUNCHED(2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -324,32 +401,30 @@ k_als_mul(const int* __restrict__ owner, const int* __restrict__ other,
     if (valid) y[my_r] = s;
 }
 
-// y[o*width + j] = chunk-folded sum over o's ratings (input order) of t[r] * A[r,j].
-// One warp per owner; lane l owns unknowns j = l, l+32, ...
+// partial[sg*width + j] = sequential sum over the ratings of one (owner, chunk) segment, in
+// input order, of t[r] * A[r,j].  One warp per segment; lane l owns unknowns j = l, l+32, ...
 template <int JPL>
 __global__ void __launch_bounds__(256)
-k_als_tmul(const int* __restrict__ grp_ptr, const int* __restrict__ grp_idx,
-           const int* __restrict__ other, const double* __restrict__ other_f,
-           const double* __restrict__ t, double* __restrict__ y, int owners, int width,
-           int other_stride, int k, const int* __restrict__ bounds,
-           const int* __restrict__ guard) {
+k_als_seg_partial(const int* __restrict__ seg_start, int nseg, const int* __restrict__ grp_idx,
+                  const int* __restrict__ other, const double* __restrict__ other_f,
+                  const double* __restrict__ t, double* __restrict__ partial, int width,
+                  int other_stride, int k, const int* __restrict__ guard) {
     if (guard && *guard) return;
-    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (o >= owners) return;
+    const int sg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (sg >= nseg) return;
     const int lane = threadIdx.x & 31;
-    const int beg = grp_ptr[o], end = grp_ptr[o + 1];
-    double acc[JPL], tot[JPL];
+    const int beg = seg_start[sg], end = seg_start[sg + 1];
+    double acc[JPL];
 #pragma unroll
-    for (int m = 0; m < JPL; m++) { acc[m] = 0; tot[m] = 0; }
-    int c = 0, next = bounds[1];
+    for (int m = 0; m < JPL; m++) acc[m] = 0;
     for (int e0 = beg; e0 < end; e0 += 32) {
         const int e = e0 + lane;
-        int r_l = INT_MAX, oth_l = 0;
+        int oth_l = 0;
         double t_l = 0;
         if (e < end) {
-            r_l = grp_idx[e];
-            oth_l = other[r_l];
-            t_l = t[r_l];
+            const int r = grp_idx[e];
+            oth_l = other[r];
+            t_l = t[r];
         }
         const int cnt = min(32, end - e0);
         for (int i0 = 0; i0 < cnt; i0 += 4) {
@@ -367,15 +442,8 @@ k_als_tmul(const int* __restrict__ grp_ptr, const int* __restrict__ grp_idx,
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int r = __shfl_sync(0xffffffffu, r_l, (i0 + u) & 31);
                 const double tv = shfl_double(t_l, (i0 + u) & 31);
                 if (i0 + u < cnt) {
-                    if (r >= next) {  // matrix.cpp:426-448: next thread's private vector
-#pragma unroll
-                        for (int m = 0; m < JPL; m++) { tot[m] = xadd(tot[m], acc[m]); acc[m] = 0; }
-                        while (r >= bounds[c + 1]) c++;
-                        next = bounds[c + 1];
-                    }
 #pragma unroll
                     for (int m = 0; m < JPL; m++) acc[m] = xadd(acc[m], xmul(tv, a[u][m]));  // :244
                 }
@@ -385,7 +453,7 @@ k_als_tmul(const int* __restrict__ grp_ptr, const int* __restrict__ grp_idx,
 #pragma unroll
     for (int m = 0; m < JPL; m++) {
         const int j = lane + 32 * m;
-        if (j < width) y[static_cast<size_t>(o) * width + j] = xadd(tot[m], acc[m]);
+        if (j < width) partial[static_cast<size_t>(sg) * width + j] = acc[m];
     }
 }
 }  // namespace
@@ -416,26 +484,34 @@ void AlsFaithfulOp::mul(const double* d_x, double* d_y, cudaStream_t s) {
         owner_, other_, other_f_, d_x, d_y, rows, width_, other_stride_, k_, guard); MRB_LAUNCHED(1);
 }
 
-void AlsFaithfulOp::tmul(const double* d_t, double* d_y, const int* d_row_bounds, int /*nchunks*/,
+void AlsFaithfulOp::tmul(const double* d_t, double* d_y, const int* d_row_bounds, int nchunks,
                          cudaStream_t s) {
     if (owners_ == 0) return;
-    const int grid = ceil_div(static_cast<long long>(owners_) * 32, 256);
+    SegTable& st = seg_[nchunks == 1 ? 1 : 0];
+    if (st.bounds_key != d_row_bounds || st.nchunks_key != nchunks)
+        build_segments(st, grp_ptr_, grp_idx_, owners_, rows, d_row_bounds, nchunks, width_, s);
+    const int grid = ceil_div(static_cast<long long>(st.nseg > 0 ? st.nseg : 1) * 32, 256);
     const int jpl = (width_ + 31) / 32;
-#define MRB_TMUL(J)                                                                         \
-    k_als_tmul<J><<<grid, 256, 0, s>>>(grp_ptr_, grp_idx_, other_, other_f_, d_t, d_y, owners_, \
-                                        width_, other_stride_, k_, d_row_bounds, guard)
-    switch (jpl) {
-        case 1: MRB_TMUL(1); break;
-        case 2: MRB_TMUL(2); break;
-        case 3: MRB_TMUL(3); break;
-        case 4: MRB_TMUL(4); break;
-        case 5: MRB_TMUL(5); break;
-        case 6: MRB_TMUL(6); break;
-        case 7: MRB_TMUL(7); break;
-        default: MRB_TMUL(8); break;
+#define MRB_TMUL(J)                                                                          \
+    k_als_seg_partial<J><<<grid, 256, 0, s>>>(st.seg_start.p, st.nseg, grp_idx_, other_, other_f_, \
+                                              d_t, st.partial.p, width_, other_stride_, k_, guard)
+    if (st.nseg > 0) {
+        switch (jpl) {
+            case 1: MRB_TMUL(1); break;
+            case 2: MRB_TMUL(2); break;
+            case 3: MRB_TMUL(3); break;
+            case 4: MRB_TMUL(4); break;
+            case 5: MRB_TMUL(5); break;
+            case 6: MRB_TMUL(6); break;
+            case 7: MRB_TMUL(7); break;
+            default: MRB_TMUL(8); break;
+        }
     }
-    MRB_LAUNCHED(1);
 #undef MRB_TMUL
+    const long long outputs = static_cast<long long>(owners_) * width_;
+    k_seg_fold<<<ceil_div(outputs, 256), 256, 0, s>>>(st.grp_seg_ptr.p, st.partial.p, d_y, outputs,
+                                                     width_, guard);
+    MRB_LAUNCHED(2);
 }
 
 }  // namespace mrb

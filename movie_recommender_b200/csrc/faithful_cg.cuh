@@ -34,6 +34,23 @@ struct FaithfulOp {
                       cudaStream_t s) = 0;
 };
 
+// Segment table of a grouped entry list against a chunk table: segment = maximal run of one
+// group's entries that fall into one reference thread chunk.  The reference's A^T t is, per
+// output, a fold over chunks of per-chunk sequential sums (matrix.cpp:418-449); the per-chunk
+// sums are independent chains, so (group, chunk) segments are the unit of parallel work and a
+// heavy group (a movie with 50 000 ratings) is spread over up to T warps instead of one.
+struct SegTable {
+    DevBuf<int> seg_start;     // [nseg + 1] first entry of each segment
+    DevBuf<int> grp_seg_ptr;   // [ngroups + 1] first segment of each group
+    DevBuf<double> partial;    // [nseg * width] per-segment sequential sums
+    int nseg = 0;
+    const int* bounds_key = nullptr;   // cache key: the chunk table it was built for
+    int nchunks_key = -1;
+};
+// d_pos: the row (or rating position) of every grouped entry, ascending inside a group.
+void build_segments(SegTable& out, const int* d_grp_ptr, const int* d_pos, int ngroups, int n,
+                    const int* d_bounds, int nchunks, int width, cudaStream_t s);
+
 struct CgResult {
     int iterations = 0;
     double final_rr = 0;
@@ -78,6 +95,7 @@ private:
     const double* vals_;
     DevBuf<int> t_ptr_, t_row_;
     DevBuf<double> t_val_;
+    SegTable seg_[2];   // [0] reference thread chunks, [1] a single chunk (explicit transpose)
 };
 
 // Implicit ALS operator (one row per rating, values gathered from the opposite side's
@@ -100,6 +118,7 @@ private:
     const double* other_f_;
     int width_, other_stride_, k_;
     bool has_one_;
+    SegTable seg_[2];
 };
 
 }  // namespace mrb

@@ -36,9 +36,11 @@ out = {"metric": "ls_rows_iterations_per_sec", "value": rows * it / (info.solve_
                     "algorithmic_bytes_per_iteration": bytes_per_it}}
 if a.faithful:
     cpp_ls.set_thread_count(os.cpu_count())
+    cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, 0.01, 2, algorithm=1, x0=x0)   # warm-up
     t0 = time.time()
     xf, itf, rrf = cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, algorithm=1, x0=x0)
-    out["faithful"] = {"iterations": itf, "e2e_s": time.time() - t0,
+    out["faithful"] = {"iterations": itf, "final_rr": rrf, "e2e_s": time.time() - t0,
+                       "thread_count": os.cpu_count(),
                        "max_abs_pred_diff_vs_native": float(np.max(np.abs((xf - x).reshape(-1))))}
 from oracle import oracle
 if oracle.has_ref():
@@ -49,6 +51,9 @@ if oracle.has_ref():
     dt = time.time() - t0
     out["cpu_baseline"] = {"value": m * itr / dt, "unit": "rows*iterations/s", "cores": os.cpu_count(),
                            "kind": "reference", "sample": "first %d rows, %d iterations, %.1f s" % (m, itr, dt)}
+    if m == rows and a.faithful:
+        out["faithful"]["bitexact_vs_reference"] = bool(
+            itf == itr and np.array_equal(xf.reshape(-1).view(np.uint64), xr.reshape(-1).view(np.uint64)))
     if m == rows:
         xs, xr = x.reshape(-1), xr.reshape(-1)
         out["parity"] = {"iterations_ref": itr, "max_abs_pred_diff": float(np.max(np.abs(
