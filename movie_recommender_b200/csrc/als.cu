@@ -74,6 +74,8 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
 }
 
 AlsProblem::~AlsProblem() {
+    for (cudaEvent_t e : gram_events_) cudaEventDestroy(e);
+    gram_events_.clear();
     gram_.reset();
     if (s_) cudaStreamDestroy(s_);
 }

@@ -2,6 +2,7 @@
 #include "../../include/cpp_ls_b200.h"
 
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "als.cuh"
@@ -48,16 +49,30 @@ static int solve_ls(int variant, int A_rows, int A_cols, const int* rowptr, cons
     cudaStream_t s;
     MRB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{s};
+    PhaseTimer t_all("cg_least_squares total");
     DevBuf<int> d_rowptr(static_cast<size_t>(A_rows) + 1), d_col(nnz);
     DevBuf<double> d_vals(nnz), d_b(A_rows), d_x(A_cols);
-    d_rowptr.upload(rowptr, static_cast<size_t>(A_rows) + 1, s);
-    d_col.upload(colidx, nnz, s);
-    d_vals.upload(vals, nnz, s);
-    d_b.upload(b, A_rows, s);
-    d_x.upload(x, A_cols, s);
-    CsrFaithfulOp op(A_rows, A_cols, nnz, d_rowptr.p, d_col.p, d_vals.p, s);
+    {
+        PhaseTimer t("  alloc + upload");
+        d_rowptr.upload(rowptr, static_cast<size_t>(A_rows) + 1, s);
+        d_col.upload(colidx, nnz, s);
+        d_vals.upload(vals, nnz, s);
+        d_b.upload(b, A_rows, s);
+        d_x.upload(x, A_cols, s);
+    }
+    std::unique_ptr<CsrFaithfulOp> op_holder;
+    {
+        PhaseTimer t("  stable transpose");
+        op_holder.reset(new CsrFaithfulOp(A_rows, A_cols, nnz, d_rowptr.p, d_col.p, d_vals.p, s));
+    }
+    CsrFaithfulOp& op = *op_holder;
     FaithfulCG cg(A_rows, A_cols, g_thread_count, s);
-    CgResult r = cg.solve(op, d_b.p, d_x.p, min_r_decrease, max_iteration, variant);
+    CgResult r;
+    {
+        PhaseTimer t("  solve");
+        r = cg.solve(op, d_b.p, d_x.p, min_r_decrease, max_iteration, variant);
+    }
+    PhaseTimer t_dl("  download + teardown");
     d_x.download(x, A_cols, s);
     MRB_CUDA(cudaStreamSynchronize(s));
     if (final_rr) *final_rr = r.final_rr;
