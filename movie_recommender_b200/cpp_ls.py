@@ -192,6 +192,11 @@ class AlsProblem:
         _lib.check(_dll.mrb_als_get_factors(self._h, _lib.dp(uf), _lib.dp(itf)))
         return uf, itf
 
+    def get_factors_synced(self):
+        """get_factors after work enqueued on the legacy default stream (half_sweep(..., 0))."""
+        self.shard_sse(0)          # synchronises stream 0
+        return self.get_factors()
+
     def get_index(self):
         """(u_ptr, u_idx, i_ptr, i_idx): the stable groupings of rating positions (K4)."""
         n = max(len(self._ratings), 1)
