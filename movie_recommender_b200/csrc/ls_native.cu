@@ -10,6 +10,9 @@
 //   2*nnz_A*(8+4) + (rows+cols+2)*4 + rows*8 + nnz_A*8 + 7*cols*8.
 #include "ls_native.cuh"
 
+#include <vector>
+
+#include "faithful_cg.cuh"
 #include "index_build.cuh"
 #include "native_cg.cuh"
 
@@ -44,6 +47,46 @@ k_csr_mul_warp(const int* __restrict__ rowptr, const int* __restrict__ colidx,
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (lane == 0) y[r] = s;
+}
+
+// One warp per (column, row-block) segment: lanes stride over the segment, fixed-order xor
+// reduction.  Splitting the rows into 64 equal blocks bounds the longest segment, so that a movie
+// column with 55 000 entries is spread over 64 warps instead of serialising one.
+__global__ void __launch_bounds__(256)
+k_csc_seg_native(const int* __restrict__ seg_start, int nseg, const int* __restrict__ t_row,
+                 const double* __restrict__ t_val, const double* __restrict__ t,
+                 double* __restrict__ partial, const CgState* __restrict__ guard) {
+    if (guard && guard->done) return;
+    const int sg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (sg >= nseg) return;
+    const int lane = threadIdx.x & 31;
+    const int beg = seg_start[sg], end = seg_start[sg + 1];
+    double s0 = 0, s1 = 0;
+    int e = beg + lane;
+    for (; e + 32 < end; e += 64) {
+        s0 += t_val[e] * t[t_row[e]];
+        s1 += t_val[e + 32] * t[t_row[e + 32]];
+    }
+    if (e < end) s0 += t_val[e] * t[t_row[e]];
+    double s = s0 + s1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) partial[sg] = s;
+}
+
+// out[c] = sum of the column's segment sums in block order; dots[c] = v[c] * out[c]
+__global__ void __launch_bounds__(256)
+k_csc_fold_native(const int* __restrict__ grp_seg_ptr, const double* __restrict__ partial,
+                  const double* __restrict__ v, double* __restrict__ out, double* __restrict__ dots,
+                  int cols, const CgState* __restrict__ guard) {
+    if (guard && guard->done) return;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double s = 0;
+    const int se = grp_seg_ptr[c + 1];
+    for (int sg = grp_seg_ptr[c]; sg < se; sg++) s += partial[sg];
+    out[c] = s;
+    if (dots) dots[c] = v ? v[c] * s : 0.0;
 }
 
 // out[c] = sum over column c of val * t[row]; dots[c] = v[c] * out[c] (v may be null)
@@ -115,11 +158,23 @@ LsNativeResult solve_ls_native(int rows, int cols, const int* rowptr, const int*
                                                                  out, rows, guard);
         MRB_LAUNCHED(1);
     };
+    // row blocks for the segment split (any fixed table gives a deterministic summation order)
+    constexpr int kRowBlocks = 64;
+    std::vector<int> h_bounds(kRowBlocks + 1);
+    for (int i = 0; i <= kRowBlocks; i++) h_bounds[i] = static_cast<int>(static_cast<long long>(rows) * i / kRowBlocks);
+    DevBuf<int> d_bounds(kRowBlocks + 1);
+    d_bounds.upload(h_bounds.data(), kRowBlocks + 1, s);
+    MRB_CUDA(cudaStreamSynchronize(s));
+    SegTable seg;
+    build_segments(seg, t_ptr.p, t_row.p, cols, nnz, d_bounds.p, kRowBlocks, 1, s);
     auto tmul = [&](const double* t, const double* v, double* out, double* dd, const CgState* guard) {
         if (cols == 0) return;
-        k_csc_tmul_warp<<<ceil_div(static_cast<long long>(cols) * 32, 256), 256, 0, s>>>(
-            t_ptr.p, t_row.p, t_val.p, t, v, out, dd, cols, guard);
-        MRB_LAUNCHED(1);
+        if (seg.nseg > 0)
+            k_csc_seg_native<<<ceil_div(static_cast<long long>(seg.nseg) * 32, 256), 256, 0, s>>>(
+                seg.seg_start.p, seg.nseg, t_row.p, t_val.p, t, seg.partial.p, guard);
+        k_csc_fold_native<<<ceil_div(cols, 256), 256, 0, s>>>(seg.grp_seg_ptr.p, seg.partial.p, v, out,
+                                                            dd, cols, guard);
+        MRB_LAUNCHED(2);
     };
     tmul(d_b.p, nullptr, g.p, nullptr, nullptr);                    // g = A^T b   (matrix.cpp:465)
     auto apply = [&](const double* v, double* out, const CgState* guard) {
