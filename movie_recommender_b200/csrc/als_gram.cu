@@ -435,6 +435,215 @@ k_gram(const GramArgs A) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Wide ranks (augmented order above 56, i.e. k > 54; config 5 has k = 128): the 153 lower tiles
+// of a k = 128 Gram matrix do not fit one warp's registers, so the matrix is produced block by
+// block -- k_gram_block accumulates a 4 x 7 rectangle of 8x8 tiles per (owner, block) work item
+// with the same gather + DMMA loop and stores it to HBM -- and k_chol_solve factors every stored
+// matrix in shared memory (one CTA per owner).  Owners are processed in batches so that the
+// stored matrices never exceed a few GB.  Generality first: this path re-gathers the factor rows
+// once per block and its Cholesky is scalar.
+// ------------------------------------------------------------------------------------------
+constexpr int GB_R = 4, GB_C = 7;          // tile rows x tile columns per block
+constexpr int GB_MAX_BLOCKS = 64;
+
+struct GramBlockArgs {
+    const int* ptr;             // CSR pointers of the side (grouped rating positions)
+    const int* owner_order;     // owners of this batch (LPT order)
+    int n_owners;               // owners in the batch
+    int n_blocks;
+    int block_r0[GB_MAX_BLOCKS], block_c0[GB_MAX_BLOCKS];   // first tile row / column
+    int* work_counter;
+    const int* other_g;
+    const double* rating_g;
+    const double* other_f;
+    int other_stride, k, n;
+    double* G;                  // [batch position or owner][n*n]
+    double* g;                  // [..][n]
+    double* corner;             // [..]  sum b^2
+    int by_owner;               // index the outputs by owner id (algorithm 3) instead of batch position
+};
+
+template <bool USER>
+__device__ __forceinline__ double aug_elem_full(const double* __restrict__ row, double rating,
+                                                int j, int k) {
+    if (j < k) return row[j];
+    if (USER) return j == k ? 1.0 : (j == k + 1 ? rating : 0.0);
+    return j == k ? rating - row[k] : 0.0;
+}
+
+template <bool USER>
+__global__ void __launch_bounds__(GRAM_WARPS * 32)
+k_gram_block(const GramBlockArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int q = lane & 3, p = lane >> 2;
+    const int n = A.n, k = A.k;
+    const int total = A.n_owners * A.n_blocks;
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(A.work_counter, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= total) break;
+        const int oi = w / A.n_blocks, b = w - oi * A.n_blocks;
+        const int owner = A.owner_order[oi];
+        const int r0 = A.block_r0[b], c0 = A.block_c0[b];
+        const int beg = A.ptr[owner], cnt = A.ptr[owner + 1] - beg;
+        double acc[GB_R * GB_C][2];
+#pragma unroll
+        for (int t = 0; t < GB_R * GB_C; t++) { acc[t][0] = 0; acc[t][1] = 0; }
+        const int nsteps = (cnt + 3) >> 2;
+        int ids_cur = 0, ids_nxt = 0;
+        double rts_cur = 0, rts_nxt = 0;
+        if (lane < cnt) { ids_cur = A.other_g[beg + lane]; rts_cur = A.rating_g[beg + lane]; }
+        if (32 + lane < cnt) { ids_nxt = A.other_g[beg + 32 + lane]; rts_nxt = A.rating_g[beg + 32 + lane]; }
+        auto fetch = [&](double (&fr)[GB_R], double (&fc)[GB_C], int st, int batch_of_cur) {
+            const bool from_next = (st >> 3) != batch_of_cur;
+            const int src = ((st & 7) << 2) + q;
+            const int id = __shfl_sync(0xffffffffu, from_next ? ids_nxt : ids_cur, src);
+            const double rt = shfl_double(from_next ? rts_nxt : rts_cur, src);
+            const bool valid = (st << 2) + q < cnt;
+            const double* row = A.other_f + static_cast<size_t>(id) * A.other_stride;
+#pragma unroll
+            for (int i = 0; i < GB_R; i++) fr[i] = valid ? aug_elem_full<USER>(row, rt, (r0 + i) * 8 + p, k) : 0.0;
+#pragma unroll
+            for (int j = 0; j < GB_C; j++) fc[j] = valid ? aug_elem_full<USER>(row, rt, (c0 + j) * 8 + p, k) : 0.0;
+        };
+        double fr1[GB_R], fc1[GB_C];
+        fetch(fr1, fc1, 0, 0);
+        for (int step = 0; step < nsteps; step++) {
+            double fr[GB_R], fc[GB_C];
+#pragma unroll
+            for (int i = 0; i < GB_R; i++) fr[i] = fr1[i];
+#pragma unroll
+            for (int j = 0; j < GB_C; j++) fc[j] = fc1[j];
+            if (((step + 1) & 7) == 0) {   // entering the next 32-rating batch with the prefetch
+                ids_cur = ids_nxt;
+                rts_cur = rts_nxt;
+                const int e = ((step + 1) << 2) + 32 + lane;
+                ids_nxt = 0;
+                rts_nxt = 0;
+                if (e < cnt) { ids_nxt = A.other_g[beg + e]; rts_nxt = A.rating_g[beg + e]; }
+            }
+            if (step + 1 < nsteps) fetch(fr1, fc1, step + 1, (step + 1) >> 3);
+#pragma unroll
+            for (int i = 0; i < GB_R; i++)
+#pragma unroll
+                for (int j = 0; j < GB_C; j++)
+                    dmma884(acc[i * GB_C + j][0], acc[i * GB_C + j][1], fr[i], fc[j]);
+        }
+        // store the lower-triangular tiles of the block (both triangles of G via the mirror)
+        const size_t slot = A.by_owner ? static_cast<size_t>(owner) : static_cast<size_t>(oi);
+        double* Go = A.G + slot * n * n;
+        double* go = A.g + slot * n;
+#pragma unroll
+        for (int i = 0; i < GB_R; i++)
+#pragma unroll
+            for (int j = 0; j < GB_C; j++) {
+                const int ti = r0 + i, tj = c0 + j;
+                if (ti < tj) continue;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int row = ti * 8 + p, col = tj * 8 + 2 * q + h;
+                    const double v = acc[i * GB_C + j][h];
+                    if (row < n && col < n) {
+                        Go[static_cast<size_t>(row) * n + col] = v;
+                        if (ti != tj) Go[static_cast<size_t>(col) * n + row] = v;
+                    }
+                    if (row == n && col < n) go[col] = v;
+                    if (row == n && col == n) A.corner[slot] = v;
+                }
+            }
+    }
+}
+
+struct CholArgs {
+    const int* owner_order;
+    int n_owners, n;
+    const double* G;
+    const double* g;
+    const double* corner;
+    double* x;
+    double* sse_out;
+    double* x_peers[8];
+    int n_peers;
+};
+
+// One CTA per owner: correction-form normal equations, right-looking Cholesky with pivot skipping
+// in shared memory, back substitution -- the same mathematics as gram_solve.
+__global__ void __launch_bounds__(128)
+k_chol_solve(const CholArgs A) {
+    extern __shared__ double sm[];
+    const int n = A.n, LD = n + 1 + ((n + 1) % 2 == 0 ? 1 : 0);   // odd leading dimension
+    double* S = sm;                         // (n+1) x LD, row n = rhs
+    double* x0 = S + static_cast<size_t>(n + 1) * LD;
+    double* d0 = x0 + n;
+    double* dl = d0 + n;
+    __shared__ double s_gdot;
+    const int oi = blockIdx.x;
+    const int owner = A.owner_order[oi];
+    const double* Go = A.G + static_cast<size_t>(oi) * n * n;
+    double* xo = A.x + static_cast<size_t>(owner) * n;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < n * n; e += nt) S[(e / n) * LD + (e % n)] = Go[e];
+    for (int c = tid; c < n; c += nt) {
+        S[n * LD + c] = A.g[static_cast<size_t>(oi) * n + c];
+        x0[c] = xo[c];
+    }
+    if (tid == 0) { S[n * LD + n] = A.corner[oi]; s_gdot = 0; }
+    __syncthreads();
+    // rhs' = g - G x0 ; the terms of x0 . (g + g') are staged in dl and summed in fixed order
+    for (int c = tid; c < n; c += nt) {
+        const double g0 = S[n * LD + c];
+        double r = g0;
+        for (int i = 0; i < n; i++) r -= S[i * LD + c] * x0[i];
+        d0[c] = S[c * LD + c];
+        dl[c] = x0[c] * (g0 + r);
+        S[n * LD + c] = r;        // row n is only read by its own column's thread here
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0;
+        for (int c = 0; c < n; c++) t += dl[c];
+        s_gdot = t;
+    }
+    __syncthreads();
+    for (int j = 0; j < n; j++) {
+        const double d = S[j * LD + j];
+        const bool ok = d > 1e-12 * d0[j] && d0[j] > 0.0;
+        const double inv = ok ? 1.0 / sqrt(d) : 0.0;
+        __syncthreads();
+        for (int i = j + tid; i <= n; i += nt) {
+            if (i == j) S[j * LD + j] = ok ? d * inv : 0.0;
+            else S[i * LD + j] = ok ? S[i * LD + j] * inv : 0.0;
+        }
+        __syncthreads();
+        if (ok) {
+            const int R = n - j;                     // rows j+1 .. n
+            for (int idx = tid; idx < R * R; idx += nt) {
+                const int i = j + 1 + idx / R, c = j + 1 + idx % R;
+                if (c <= i) S[i * LD + c] -= S[i * LD + j] * S[c * LD + j];   // includes the corner (n, n)
+            }
+        }
+        __syncthreads();
+    }
+    // residual sum of squares at the solution: updated corner - x0.(g + g')
+    if (tid == 0 && A.sse_out) A.sse_out[owner] = S[n * LD + n] - s_gdot;
+    // back substitution L^T delta = y (row n), column oriented
+    for (int j = n - 1; j >= 0; j--) {
+        const double Ljj = S[j * LD + j];
+        const double dj = Ljj != 0.0 ? S[n * LD + j] / Ljj : 0.0;
+        __syncthreads();
+        if (tid == 0) dl[j] = dj;
+        for (int c = tid; c < j; c += nt) S[n * LD + c] -= S[j * LD + c] * dj;
+        __syncthreads();
+    }
+    for (int c = tid; c < n; c += nt) {
+        const double v = x0[c] + dl[c];
+        xo[c] = v;
+        for (int pj = 0; pj < A.n_peers; pj++) A.x_peers[pj][static_cast<size_t>(owner) * n + c] = v;
+    }
+}
+
 // Sum of squared training errors, deterministic: per-CTA partials in fixed tree order.
 __global__ void __launch_bounds__(256)
 k_sse_partials(const int* __restrict__ user_ids, const int* __restrict__ item_ids,
@@ -516,6 +725,8 @@ struct Side {
     int n_multi = 0;
     int n_slots = 0;
     int lo = 0, hi = 0;   // owner range of this rank
+    DevBuf<int> owner_order;   // owners with ratings, longest first (wide-rank path)
+    int n_owner_items = 0;
 };
 
 void build_side(Side& sd, const int* d_ptr, const int* d_idx, const int* d_other_ids,
@@ -570,6 +781,18 @@ void build_side(Side& sd, const int* d_ptr, const int* d_idx, const int* d_other
         }
         if (nseg > 1) { sd.n_multi++; sd.n_slots += nseg; }
     }
+    {
+        std::vector<int> nonempty;
+        nonempty.reserve(order.size());
+        for (int o : order)
+            if (ptr[o + 1] > ptr[o]) nonempty.push_back(o);
+        sd.n_owner_items = static_cast<int>(nonempty.size());
+        sd.owner_order.alloc(std::max<size_t>(nonempty.size(), 1));
+        if (!nonempty.empty())
+            MRB_CUDA(cudaMemcpyAsync(sd.owner_order.p, nonempty.data(), sizeof(int) * nonempty.size(),
+                                     cudaMemcpyHostToDevice, s));
+        MRB_CUDA(cudaStreamSynchronize(s));
+    }
     sd.n_work = static_cast<int>(work.size());
     sd.work.alloc(work.size());
     MRB_CUDA(cudaMemcpyAsync(sd.work.p, work.data(), sizeof(WorkItem) * work.size(),
@@ -618,6 +841,7 @@ namespace {
 // dots, then one fixed-order reduction.
 // ------------------------------------------------------------------------------------------
 
+template <int NPL>   // unknowns per lane: n <= 32 * NPL
 __global__ void __launch_bounds__(256)
 k_block_matvec(const double* __restrict__ G, const double* __restrict__ v, double* __restrict__ out,
                double* __restrict__ dots, int owners, int n, const CgState* __restrict__ guard) {
@@ -627,20 +851,31 @@ k_block_matvec(const double* __restrict__ G, const double* __restrict__ v, doubl
     const int lane = threadIdx.x & 31;
     const double* Go = G + static_cast<size_t>(o) * n * n;
     const double* vo = v + static_cast<size_t>(o) * n;
-    const bool has0 = lane < n, has1 = lane + 32 < n;
-    const double v0 = has0 ? vo[lane] : 0.0, v1 = has1 ? vo[lane + 32] : 0.0;
-    double y0 = 0, y1 = 0;
+    double vv[NPL], y[NPL];
+#pragma unroll
+    for (int m = 0; m < NPL; m++) {
+        vv[m] = lane + 32 * m < n ? vo[lane + 32 * m] : 0.0;
+        y[m] = 0;
+    }
+#pragma unroll
+    for (int mj = 0; mj < NPL; mj++) {
+        const int jn = min(32, n - 32 * mj);
 #pragma unroll 4
-    for (int j = 0; j < n; j++) {
-        const double vj = shfl_double(j < 32 ? v0 : v1, j & 31);
-        const double* row = Go + static_cast<size_t>(j) * n;
-        if (has0) y0 += row[lane] * vj;
-        if (has1) y1 += row[lane + 32] * vj;
+        for (int jj = 0; jj < jn; jj++) {
+            const double vj = shfl_double(vv[mj], jj);
+            const double* row = Go + static_cast<size_t>(32 * mj + jj) * n;
+#pragma unroll
+            for (int m = 0; m < NPL; m++)
+                if (lane + 32 * m < n) y[m] += row[lane + 32 * m] * vj;
+        }
     }
     double* oo = out + static_cast<size_t>(o) * n;
-    if (has0) oo[lane] = y0;
-    if (has1) oo[lane + 32] = y1;
-    double d = v0 * y0 + v1 * y1;
+    double d = 0;
+#pragma unroll
+    for (int m = 0; m < NPL; m++) {
+        if (lane + 32 * m < n) oo[lane + 32 * m] = y[m];
+        d += vv[m] * y[m];
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
     if (lane == 0) dots[o] = d;
@@ -657,6 +892,10 @@ struct AlsProblem::GramState {
     int sms = 148;
     int st_doubles = 0;
     int built_rank = -1, built_world = -1;
+    // wide ranks (k > 54): per-batch stored matrices of the block-Gram + shared-memory Cholesky path
+    bool wide = false;
+    DevBuf<double> wG, wg, wcorner;
+    int wide_batch = 0;
     // algorithm 3 (Gram block-CG): stored blocks and CG vectors, sized for the larger side
     DevBuf<double> G, g, r, p, Ap, dots, cg_partials;
     DevBuf<FaithfulCG::State> cg_state;
@@ -665,7 +904,7 @@ struct AlsProblem::GramState {
 void AlsProblem::ensure_gram() {
     const int n_u = k_ + 1;
     const int m8 = (n_u + 1 + 7) / 8;
-    MRB_REQUIRE(m8 <= 7, "als algorithm 3/4: rank above 54 is not supported yet");
+    MRB_REQUIRE(n_u <= 160, "als algorithm 3/4: rank above 159 is not supported");
     if (gram_ && gram_->built_rank == rank_ && gram_->built_world == world_) return;
     PhaseTimer t_g("ensure_gram (work lists)");
     gram_ = std::make_shared<GramState>();
@@ -675,9 +914,18 @@ void AlsProblem::ensure_gram() {
     MRB_CUDA(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, dev));
     build_side(g.user, u_ptr_.p, u_idx_.p, item_ids_.p, ratings_.p, nu_, nnz_, rank_, world_, s_);
     build_side(g.item, i_ptr_.p, i_idx_.p, user_ids_.p, ratings_.p, ni_, nnz_, rank_, world_, s_);
-    g.st_doubles = m8 * (m8 + 1) / 2 * 64;
-    const int slots = std::max(g.user.n_slots, g.item.n_slots);
+    g.wide = m8 > 7;
+    g.st_doubles = g.wide ? 1 : m8 * (m8 + 1) / 2 * 64;
+    const int slots = g.wide ? 1 : std::max(g.user.n_slots, g.item.n_slots);
     g.partials.alloc(static_cast<size_t>(std::max(slots, 1)) * g.st_doubles);
+    if (g.wide) {
+        const size_t nn = static_cast<size_t>(n_u) * n_u;
+        const size_t items = static_cast<size_t>(std::max(std::max(g.user.n_owner_items, g.item.n_owner_items), 1));
+        g.wide_batch = static_cast<int>(std::max<size_t>(1, std::min(items, (size_t(2) << 30) / (nn * 8))));
+        g.wG.alloc(static_cast<size_t>(g.wide_batch) * nn);
+        g.wg.alloc(static_cast<size_t>(g.wide_batch) * n_u);
+        g.wcorner.alloc(std::max<size_t>(std::max<size_t>(g.wide_batch, nu_), ni_) + 1);
+    }
     g.counters.alloc(1 + static_cast<size_t>(std::max(std::max(g.user.n_multi, g.item.n_multi), 1)));
     g.sse_partials.alloc(1024);
     g.sse_owner.alloc(static_cast<size_t>(std::max(ni_, 1)));
@@ -689,6 +937,94 @@ void AlsProblem::ensure_gram() {
 void AlsProblem::launch_half(bool user_side, cudaStream_t stream, int epilogue) {
     GramState& g = *gram_;
     Side& sd = user_side ? g.user : g.item;
+    if (g.wide) {
+        // ---- wide ranks: block Gram to HBM, then one shared-memory Cholesky per owner
+        const int n = user_side ? k_ + 1 : k_;
+        const int m8 = (n + 1 + 7) / 8;
+        GramBlockArgs a{};
+        a.n_blocks = 0;
+        for (int r0 = 0; r0 < m8; r0 += GB_R)
+            for (int c0 = 0; c0 < m8; c0 += GB_C)
+                if (r0 + GB_R - 1 >= c0) {
+                    MRB_REQUIRE(a.n_blocks < GB_MAX_BLOCKS, "als: too many tile blocks");
+                    a.block_r0[a.n_blocks] = r0;
+                    a.block_c0[a.n_blocks] = c0;
+                    a.n_blocks++;
+                }
+        a.ptr = user_side ? u_ptr_.p : i_ptr_.p;
+        a.work_counter = g.counters.p;
+        a.other_g = sd.other_g.p;
+        a.rating_g = sd.rating_g.p;
+        a.other_f = user_side ? itf_.p : uf_.p;
+        a.other_stride = user_side ? k_ : k_ + 1;
+        a.k = k_;
+        a.n = n;
+        CholArgs c{};
+        c.n = n;
+        c.x = user_side ? uf_.p : itf_.p;
+        c.n_peers = 0;
+        const std::vector<double*>& peers = user_side ? uf_peers_ : itf_peers_;
+        for (size_t j = 0; j < peers.size(); j++)
+            if (static_cast<int>(j) != rank_ && peers[j] != nullptr && c.n_peers < 8)
+                c.x_peers[c.n_peers++] = peers[j];
+        if (!user_side) {
+            MRB_CUDA(cudaMemsetAsync(g.sse_owner.p, 0, sizeof(double) * g.sse_owner.n, stream));
+            c.sse_out = g.sse_owner.p;
+        }
+        if (sd.n_owner_items == 0) return;
+        static int per_sm_u = 0, per_sm_i = 0;
+        int& per_sm = user_side ? per_sm_u : per_sm_i;
+        if (per_sm == 0) {
+            if (user_side) MRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gram_block<true>, GRAM_WARPS * 32, 0));
+            else MRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gram_block<false>, GRAM_WARPS * 32, 0));
+        }
+        const int LD = n + 1 + ((n + 1) % 2 == 0 ? 1 : 0);
+        const size_t chol_smem = sizeof(double) * (static_cast<size_t>(n + 1) * LD + 3 * n);
+        MRB_CUDA(cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(chol_smem)));
+        cudaEvent_t e0, e1;
+        MRB_CUDA(cudaEventCreate(&e0));
+        MRB_CUDA(cudaEventCreate(&e1));
+        MRB_CUDA(cudaEventRecord(e0, stream));
+        const bool store = epilogue == EPI_STORE;
+        if (store) {
+            const size_t owners = user_side ? nu_ : ni_;
+            MRB_CUDA(cudaMemsetAsync(g.G.p, 0, sizeof(double) * owners * n * n, stream));
+            MRB_CUDA(cudaMemsetAsync(g.g.p, 0, sizeof(double) * owners * n, stream));
+        }
+        const int batch = store ? sd.n_owner_items : g.wide_batch;
+        for (int b0 = 0; b0 < sd.n_owner_items; b0 += batch) {
+            const int cnt = std::min(batch, sd.n_owner_items - b0);
+            a.owner_order = sd.owner_order.p + b0;
+            a.n_owners = cnt;
+            a.G = store ? g.G.p : g.wG.p;
+            a.g = store ? g.g.p : g.wg.p;
+            a.corner = g.wcorner.p;
+            a.by_owner = store ? 1 : 0;
+            MRB_CUDA(cudaMemsetAsync(g.counters.p, 0, sizeof(int), stream));
+            const long long total = static_cast<long long>(cnt) * a.n_blocks;
+            const int grid = static_cast<int>(std::min<long long>(static_cast<long long>(g.sms) * per_sm,
+                                                                  (total + GRAM_WARPS - 1) / GRAM_WARPS));
+            if (user_side) k_gram_block<true><<<grid, GRAM_WARPS * 32, 0, stream>>>(a);
+            else k_gram_block<false><<<grid, GRAM_WARPS * 32, 0, stream>>>(a);
+            MRB_LAUNCHED(1);
+            MRB_CUDA(cudaGetLastError());
+            if (!store) {
+                c.owner_order = a.owner_order;
+                c.n_owners = cnt;
+                c.G = g.wG.p;
+                c.g = g.wg.p;
+                c.corner = g.wcorner.p;
+                k_chol_solve<<<cnt, 128, chol_smem, stream>>>(c);
+                MRB_LAUNCHED(1);
+                MRB_CUDA(cudaGetLastError());
+            }
+        }
+        MRB_CUDA(cudaEventRecord(e1, stream));
+        gram_events_.push_back(e0);
+        gram_events_.push_back(e1);
+        return;
+    }
     MRB_CUDA(cudaMemsetAsync(g.counters.p, 0, sizeof(int) * g.counters.n, stream));
     GramArgs a{};
     a.work = sd.work.p;
@@ -855,7 +1191,16 @@ static CgResult block_cg_solve(AlsProblem::GramState& g, double* x, int owners, 
     NativeCgWorkspace ws{g.r.p, g.p.p, g.Ap.p, g.dots.p, g.cg_partials.p, g.cg_state.p};
     // A^T A v for the block-diagonal normal matrix; dots[o] = v_o . (G_o v_o)
     auto apply = [&](const double* v, double* out, const CgState* guard) {
-        k_block_matvec<<<mb, 256, 0, s>>>(g.G.p, v, out, g.dots.p, owners, n, guard);
+        switch ((n + 31) / 32) {
+            case 1: k_block_matvec<1><<<mb, 256, 0, s>>>(g.G.p, v, out, g.dots.p, owners, n, guard); break;
+            case 2: k_block_matvec<2><<<mb, 256, 0, s>>>(g.G.p, v, out, g.dots.p, owners, n, guard); break;
+            case 3: k_block_matvec<3><<<mb, 256, 0, s>>>(g.G.p, v, out, g.dots.p, owners, n, guard); break;
+            case 4: k_block_matvec<4><<<mb, 256, 0, s>>>(g.G.p, v, out, g.dots.p, owners, n, guard); break;
+            case 5: k_block_matvec<5><<<mb, 256, 0, s>>>(g.G.p, v, out, g.dots.p, owners, n, guard); break;
+            case 6: k_block_matvec<6><<<mb, 256, 0, s>>>(g.G.p, v, out, g.dots.p, owners, n, guard); break;
+            case 7: k_block_matvec<7><<<mb, 256, 0, s>>>(g.G.p, v, out, g.dots.p, owners, n, guard); break;
+            default: k_block_matvec<8><<<mb, 256, 0, s>>>(g.G.p, v, out, g.dots.p, owners, n, guard); break;
+        }
         MRB_LAUNCHED(1);
     };
     // inside als() the inner solves always use (0.01, 200)            (matrix.cpp:818, 854-855)

@@ -186,3 +186,39 @@ def test_gram_cg_rows_without_ratings_and_determinism(require_gpu, cpp_ls):
                    user_factors=uf0, item_factors=if0)
     assert bits_equal(a[0], b[0]) and bits_equal(a[1], b[1])
     assert bits_equal(a[0][60 * 6:], uf0[60 * 6:]) and bits_equal(a[1][70 * 5:], if0[70 * 5:])
+
+
+# ------------------------------------------------------------------------------------------------
+# Wide ranks (k > 54; config 5 uses k = 128): block-wise Gram to HBM + shared-memory Cholesky.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nu,ni,nnz,k", [(150, 120, 14000, 64), (300, 260, 70000, 128), (90, 80, 7000, 55)])
+def test_wide_rank_cholesky_matches_numpy_exact_als(require_gpu, cpp_ls, oracle, nu, ni, nnz, k):
+    p = synth.als_problem(nu, ni, nnz, k, seed=k)
+    args = (p["user_ids"], p["item_ids"], p["ratings"], k)
+    with cpp_ls.AlsProblem(*args, nu, ni) as prob:
+        prob.set_factors(p["user_factors0"], p["item_factors0"])
+        info = prob.run(4, -1e300, 1)
+        uf, itf = prob.get_factors()
+    ru, ri = numpy_half_sweeps(p, p["user_factors0"], p["item_factors0"], sweeps=1)
+    u, i = p["user_ids"], p["item_ids"]
+    pa = (uf.reshape(nu, k + 1)[u, :k] * itf.reshape(ni, k)[i]).sum(1) + uf.reshape(nu, k + 1)[u, k]
+    pb = (ru.reshape(nu, k + 1)[u, :k] * ri.reshape(ni, k)[i]).sum(1) + ru.reshape(nu, k + 1)[u, k]
+    assert np.max(np.abs(pa - pb)) < 1e-6
+    # the SSE derived from the factorisation equals the oracle's evaluation
+    rmse = oracle.rmse(*args, uf, itf)
+    assert abs(np.sqrt(info.last_rr / len(u)) - rmse) < 1e-8
+
+
+def test_wide_rank_gram_cg_first_sweep(require_gpu, cpp_ls, oracle):
+    nu, ni, nnz, k = 400, 300, 100000, 64       # ~4x more ratings per row than unknowns
+    p = synth.als_problem(nu, ni, nnz, k, seed=64)
+    args = (p["user_ids"], p["item_ids"], p["ratings"], k)
+    uo, io, _ = oracle.als(*args, p["user_factors0"], p["item_factors0"], -1e300, 1, 1, 1)
+    with cpp_ls.AlsProblem(*args, nu, ni) as prob:
+        prob.set_factors(p["user_factors0"], p["item_factors0"])
+        info = prob.run(3, -1e300, 1)
+        uf, itf = prob.get_factors()
+    d = abs(oracle.rmse(*args, uf, itf) - oracle.rmse(*args, uo, io))
+    print("wide gram-cg: cg iterations", info.cg_iterations, "rmse diff", d,
+          "factor rel err", rel_err(uf, uo), rel_err(itf, io))
+    assert d < 1e-6
