@@ -570,7 +570,7 @@ struct CholArgs {
 
 // One CTA per owner: correction-form normal equations, right-looking Cholesky with pivot skipping
 // in shared memory, back substitution -- the same mathematics as gram_solve.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 k_chol_solve(const CholArgs A) {
     extern __shared__ double sm[];
     const int n = A.n, LD = n + 1 + ((n + 1) % 2 == 0 ? 1 : 0);   // odd leading dimension
@@ -618,10 +618,12 @@ k_chol_solve(const CholArgs A) {
         }
         __syncthreads();
         if (ok) {
-            const int R = n - j;                     // rows j+1 .. n
-            for (int idx = tid; idx < R * R; idx += nt) {
-                const int i = j + 1 + idx / R, c = j + 1 + idx % R;
-                if (c <= i) S[i * LD + c] -= S[i * LD + j] * S[c * LD + j];   // includes the corner (n, n)
+            // trailing update of rows j+1 .. n (row n = rhs, including the corner): one warp per
+            // row stripe, lanes along the row (conflict-free: odd leading dimension)
+            const int lane = tid & 31, wrp = tid >> 5, nw = nt >> 5;
+            for (int i = j + 1 + wrp; i <= n; i += nw) {
+                const double Lij = S[i * LD + j];
+                for (int c = j + 1 + lane; c <= i; c += 32) S[i * LD + c] -= Lij * S[c * LD + j];
             }
         }
         __syncthreads();
@@ -1015,7 +1017,7 @@ void AlsProblem::launch_half(bool user_side, cudaStream_t stream, int epilogue) 
                 c.G = g.wG.p;
                 c.g = g.wg.p;
                 c.corner = g.wcorner.p;
-                k_chol_solve<<<cnt, 128, chol_smem, stream>>>(c);
+                k_chol_solve<<<cnt, 512, chol_smem, stream>>>(c);
                 MRB_LAUNCHED(1);
                 MRB_CUDA(cudaGetLastError());
             }
