@@ -71,7 +71,9 @@ MRB_API int cg_least_squares2_from_python(int A_rows, int A_cols, int* A_row_ind
  *   algorithm 3    : (extension) the same CG with global alpha/beta and the same stopping rule,
  *                    run on per-row Gram blocks with GPU-native summation order.
  *   algorithm 4    : (extension) every half-sweep solves each row's normal equations exactly
- *                    (gathered Gram matrix + in-shared-memory Cholesky).
+ *                    (gathered Gram matrix on the fp64 tensor cores + Cholesky; register-resident
+ *                    up to rank 54, block-wise with a shared-memory Cholesky up to rank 159).
+ * Ranks: algorithms 1, 2 up to 255; algorithms 3, 4 up to 159.
  * Any other value behaves like 2, as in the reference (matrix.cpp:817-828). */
 MRB_API int als_from_python(int* user_ids, int* item_ids, int ratings_length, double* ratings_values,
                     int num_item_factors, int user_factors_length, double* user_factors_values,
