@@ -312,6 +312,15 @@ def main():
                                                       res["gram_ms"], res["launches"])
         uf, itf = res["user_factors"], res["item_factors"]
         step_ms = dev_ms / args.steps
+        runner.prob.close()
+        # e2e at N GPUs: one sharded sweep per step from page-locked HOST buffers (all ranks)
+        from movie_recommender_b200 import sharded as _sh
+        pinned = dict(p)
+        keep_alive = []
+        for key in ("user_ids", "item_ids", "ratings", "user_factors0", "item_factors0"):
+            pinned[key], t = pinned_copy(p[key])
+            keep_alive.append(t)
+        e2e_s_multi, _, _ = _sh.e2e_steps(pinned, k, nu, ni, rank, world, max(1, min(args.e2e_steps, 3)))
     value = nnz / (step_ms * 1e-3)
 
     if rank != 0:
@@ -327,6 +336,14 @@ def main():
 
     # ---------------- e2e through the drop-in call with pinned host buffers (N=1 path)
     e2e = None
+    if world > 1:
+        h2d = world * (nnz * (4 + 4 + 8) + (nu * (k + 1) + ni * k) * 8)
+        d2h = world * (nu * (k + 1) + ni * k) * 8
+        e2e = {"value": nnz / e2e_s_multi, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s_multi * 1e3,
+               "steps": max(1, min(args.e2e_steps, 3)),
+               "call": "sharded.ShardedAls(host buffers) + one sweep + get_factors per step on every "
+                       "rank (upload, index build, work lists, peer mapping exchange included)"}
     if world == 1:
         if prob is not None:
             prob.close()

@@ -127,3 +127,32 @@ class ShardedAls:
         return dict(device_ms=float(ms[0]), gram_ms=float(ms[1]), wall_ms=wall_ms, clocks=clocks,
                     launches=int(launches) * self.world, user_factors=uf, item_factors=itf,
                     sse=sse, exchange=self.exchange, ranges=self.ranges)
+
+
+def e2e_steps(problem, k, num_users, num_items, rank, world, steps, exchange="p2p"):
+    """End-to-end time of one sharded sweep from HOST buffers, per step: every rank uploads the
+    (page-locked) ratings and factors, builds its indices and work lists, exchanges the peer
+    mappings, runs one sweep and copies the factors back.  Returns seconds per step (max over
+    ranks) and the factors of the last step."""
+    import time
+
+    import torch
+    import torch.distributed as dist
+    cur = dict(problem)
+    times = []
+    for step in range(steps + 1):              # step 0 is a warm-up
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        s = ShardedAls(cur, k, num_users, num_items, rank, world, exchange=exchange)
+        s.sweep()
+        torch.cuda.synchronize()
+        dist.barrier()
+        uf, itf = s.prob.get_factors()
+        dt = torch.tensor([time.time() - t0], dtype=torch.float64, device=s.device)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        s.prob.close()
+        cur["user_factors0"], cur["item_factors0"] = uf, itf
+        if step > 0:
+            times.append(float(dt.item()))
+    return sum(times) / len(times), cur["user_factors0"], cur["item_factors0"]
