@@ -32,7 +32,7 @@ namespace {
 constexpr int SIM_C = 64;       // candidates kept per query
 constexpr int SIM_WARPS = 8;    // warps per CTA, 8 query rows each
 constexpr int SIM_ROWS = SIM_WARPS * 8;
-constexpr int SIM_CT = 64;      // columns per shared-memory stage
+constexpr int SIM_CT = 128;     // columns per shared-memory stage
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -164,27 +164,34 @@ k_sim_candidates(const double* __restrict__ Hp, int n, int q_lo, int q_hi,
         __syncthreads();
         const double* B = Bs + static_cast<size_t>(stage) * SIM_CT * KP;
 #pragma unroll 1
-        for (int ct = 0; ct < SIM_CT / 8; ct++) {
+        for (int ct = 0; ct < SIM_CT / 8; ct += 2) {
             const int col_base = blk * SIM_CT + ct * 8;
             if (col_base >= n) break;
-            double c0 = 0, c1 = 0;
-            const double* bp = B + static_cast<size_t>(ct * 8 + p) * KP + q;
+            // two column tiles at a time: two independent accumulator chains for the tensor pipe
+            double c0[2] = {0, 0}, c1[2] = {0, 0};
+            const double* bp0 = B + static_cast<size_t>(ct * 8 + p) * KP + q;
+            const double* bp1 = bp0 + 8 * KP;
 #pragma unroll
-            for (int ks = 0; ks < KS; ks++) dmma(c0, c1, a[ks], bp[4 * ks]);
-            // lane holds score(qrow, col_base + 2q) and (.., + 2q + 1)
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int col = col_base + 2 * q + h;
-                const double sc = h ? c1 : c0;
-                if (qvalid && col < n && col != qrow && sc > thr) {
-                    const int pos = atomicAdd(&sm.buf_cnt[row_local], 1);
-                    sm.score[row_local][SIM_C + pos] = sc;
-                    sm.id[row_local][SIM_C + pos] = col;
-                }
+            for (int ks = 0; ks < KS; ks++) {
+                dmma(c0[0], c1[0], a[ks], bp0[4 * ks]);
+                dmma(c0[1], c1[1], a[ks], bp1[4 * ks]);
             }
+            // lane holds score(qrow, col_base + 8 u + 2q) and (.., + 2q + 1) for u = 0, 1
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int col = col_base + 8 * u + 2 * q + h;
+                    const double sc = h ? c1[u] : c0[u];
+                    if (qvalid && col < n && col != qrow && sc > thr) {
+                        const int pos = atomicAdd(&sm.buf_cnt[row_local], 1);
+                        sm.score[row_local][SIM_C + pos] = sc;
+                        sm.id[row_local][SIM_C + pos] = col;
+                    }
+                }
             __syncwarp();
-            // a row may receive up to 8 pushes per tile: merge while 8 more still fit
-            const bool full = sm.buf_cnt[row_local] > SIM_C - 8;
+            // a row may receive up to 16 pushes per tile pair: merge while 16 more still fit
+            const bool full = sm.buf_cnt[row_local] > SIM_C - 16;
             unsigned need = __ballot_sync(0xffffffffu, full);
             while (need) {
                 const int r = (__ffs(need) - 1) >> 2;          // local row p of the first flagged lane
