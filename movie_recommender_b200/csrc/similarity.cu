@@ -77,39 +77,89 @@ struct SimSmem {
     int buf_cnt[SIM_ROWS];
 };
 
-// Merge list and pending buffer of one query row (warp-cooperative, rank counting).
+struct KV {
+    double s;
+    int id;
+};
+__device__ __forceinline__ KV kv_shfl_xor(const KV& v, int mask) {
+    KV r;
+    r.s = __shfl_xor_sync(0xffffffffu, v.s, mask);
+    r.id = __shfl_xor_sync(0xffffffffu, v.id, mask);
+    return r;
+}
+__device__ __forceinline__ KV kv_shfl(const KV& v, int src) {
+    KV r;
+    r.s = __shfl_sync(0xffffffffu, v.s, src);
+    r.id = __shfl_sync(0xffffffffu, v.id, src);
+    return r;
+}
+// of two candidates keep the one that comes first in (score desc, id asc) order, or the other
+__device__ __forceinline__ KV kv_pick(const KV& a, const KV& b, bool keep_first) {
+    return (precedes(a.s, a.id, b.s, b.id) == keep_first) ? a : b;
+}
+
+// Merge list and pending buffer of one query row (warp-cooperative, in registers): bitonic sort
+// of the <= 64 pending candidates (2 per lane), then one bitonic merge step against the sorted
+// list (list[i] vs pending[63 - i] keeps the 64 best as a bitonic sequence) and a 64-element
+// bitonic merge.  ~600 instructions instead of ~2000 for the former rank counting.
 __device__ __forceinline__ void sim_compact(SimSmem& sm, int row, int lane) {
     const int lc = sm.list_cnt[row], bc = sm.buf_cnt[row];
-    double s[4];
-    int id[4], rank[4];
-    bool valid[4];
+    const KV worst = {-1e300, 0x7fffffff};
+    KV b[2], a[2];
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-        const int slot = lane + 32 * e;
-        valid[e] = slot < SIM_C ? slot < lc : slot - SIM_C < bc;
-        s[e] = valid[e] ? sm.score[row][slot] : 0.0;
-        id[e] = valid[e] ? sm.id[row][slot] : 0;
-        rank[e] = 0;
+    for (int r = 0; r < 2; r++) {
+        const int i = lane + 32 * r;
+        b[r] = i < bc ? KV{sm.score[row][SIM_C + i], sm.id[row][SIM_C + i]} : worst;
+        a[r] = i < lc ? KV{sm.score[row][i], sm.id[row][i]} : worst;
     }
-    for (int f = 0; f < lc; f++) {
-        const double sf = sm.score[row][f];
-        const int idf = sm.id[row][f];
+    // ---- bitonic sort of the pending 64, best first; element index i = lane + 32 r
 #pragma unroll
-        for (int e = 0; e < 4; e++) rank[e] += precedes(sf, idf, s[e], id[e]) ? 1 : 0;
+    for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j >= 1; j >>= 1) {
+            if (j == 32) {
+                // partners live in the same lane (r = 0 and r = 1); k == 64 here: best first
+                const KV lo = kv_pick(b[0], b[1], true), hi = kv_pick(b[0], b[1], false);
+                b[0] = lo;
+                b[1] = hi;
+            } else {
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int i = lane + 32 * r;
+                    const KV other = kv_shfl_xor(b[r], j);
+                    const bool up = (i & k) == 0;
+                    b[r] = kv_pick(b[r], other, ((i & j) == 0) == up);
+                }
+            }
+        }
     }
-    for (int f = 0; f < bc; f++) {
-        const double sf = sm.score[row][SIM_C + f];
-        const int idf = sm.id[row][SIM_C + f];
+    // ---- list[i] vs pending[63 - i]: the 64 best of the 128, as a bitonic sequence
+    {
+        const KV p0 = kv_shfl(b[1], 31 - lane);   // pending[63 - lane]
+        const KV p1 = kv_shfl(b[0], 31 - lane);   // pending[63 - (lane + 32)]
+        a[0] = kv_pick(a[0], p0, true);
+        a[1] = kv_pick(a[1], p1, true);
+    }
+    // ---- bitonic merge of 64, best first
+    {
+        const KV lo = kv_pick(a[0], a[1], true), hi = kv_pick(a[0], a[1], false);
+        a[0] = lo;
+        a[1] = hi;
+    }
 #pragma unroll
-        for (int e = 0; e < 4; e++) rank[e] += precedes(sf, idf, s[e], id[e]) ? 1 : 0;
+    for (int j = 16; j >= 1; j >>= 1) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const KV other = kv_shfl_xor(a[r], j);
+            a[r] = kv_pick(a[r], other, (lane & j) == 0);
+        }
     }
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < 4; e++)
-        if (valid[e] && rank[e] < SIM_C) {
-            sm.score[row][rank[e]] = s[e];
-            sm.id[row][rank[e]] = id[e];
-        }
+    for (int r = 0; r < 2; r++) {
+        sm.score[row][lane + 32 * r] = a[r].s;
+        sm.id[row][lane + 32 * r] = a[r].id;
+    }
     if (lane == 0) {
         sm.list_cnt[row] = min(lc + bc, SIM_C);
         sm.buf_cnt[row] = 0;
