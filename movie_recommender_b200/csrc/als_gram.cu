@@ -90,6 +90,8 @@ struct GramArgs {
 
 enum { EPI_SOLVE = 0, EPI_STORE = 1 };
 
+__device__ double g_zero_row[64];   // zero-initialised: the factor row of a padding rating
+
 // index of lower-triangular tile (ti, tj), tj <= ti
 __host__ __device__ constexpr int TI(int ti, int tj) { return ti * (ti + 1) / 2 + tj; }
 
@@ -351,6 +353,22 @@ k_gram(const GramArgs A) {
     const int q = lane & 3, p = lane >> 2;
     const int n = A.n, k = A.k;
 
+    // Element j = 8 t + p of the augmented row [a; b] (users: a = item factors, 1 for the bias,
+    // b = rating; items: a = user factors, b = rating - user bias formed at use time).  The order
+    // n + 1 fills the last tile, so k >= 8 (M8 - 1) - 1: every tile before the last two (users) /
+    // the last one (items) is a plain load; only the NS special tiles need the per-lane choice,
+    // and that choice is fixed for the whole kernel.
+    constexpr int PLAIN = USER ? (M8 >= 2 ? M8 - 2 : 0) : M8 - 1;
+    constexpr int NS = M8 - PLAIN;
+    bool sp_load[NS], sp_one[NS], sp_rating[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const int j = 8 * (PLAIN + s) + p;
+        sp_load[s] = USER ? j < k : j <= k;
+        sp_one[s] = USER && j == k;
+        sp_rating[s] = USER && j == k + 1;
+    }
+
     for (;;) {
         int w = 0;
         if (lane == 0) w = atomicAdd(A.work_counter, 1);
@@ -376,13 +394,25 @@ k_gram(const GramArgs A) {
             // fragments of k-step `st` (ratings 4 st .. 4 st + 3); st's batch is the current or next
             const bool from_next = (st >> 3) != batch_of_cur;
             const int src = ((st & 7) << 2) + q;
-            const int id = __shfl_sync(0xffffffffu, from_next ? ids_nxt : ids_cur, src);
-            const double rt = shfl_double(from_next ? rts_nxt : rts_cur, src);
+            int id = __shfl_sync(0xffffffffu, from_next ? ids_nxt : ids_cur, src);
+            if (A.debug_skip_solve & 2) id &= 15;   // measurement only: every gather hits L1
+            const double rt = shfl_double(from_next ? rts_nxt : rts_cur, src);   // 0 past the end
             const bool valid = (st << 2) + q < cnt;
-            const double* row = A.other_f + static_cast<size_t>(id) * A.other_stride;
+            // the padding ratings of the last k-step read a row of zeros: no per-element select
+            const double* rowp = (valid ? A.other_f + static_cast<size_t>(id) * A.other_stride
+                                        : g_zero_row) + p;
 #pragma unroll
-            for (int t = 0; t < M8; t++) dst[t] = valid ? aug_elem<USER>(row, rt, t * 8 + p, k) : 0.0;
-            rt_out = valid ? rt : 0.0;
+            for (int t = 0; t < PLAIN; t++) dst[t] = rowp[8 * t];
+            // special tiles: the raw load only (or 0).  The 1 / rating / rating - bias choice is
+            // made when the fragment is USED, two k-steps later: an instruction that consumes a
+            // value just requested from memory would stall the warp for the whole latency
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                double v = 0.0;
+                if (sp_load[s]) v = rowp[8 * (PLAIN + s)];
+                dst[PLAIN + s] = v;
+            }
+            rt_out = rt;
         };
         double f1[M8], f2[M8], rt1 = 0, rt2 = 0;
         fetch(f1, rt1, 0, 0);
@@ -392,7 +422,18 @@ k_gram(const GramArgs A) {
             double f[M8];
 #pragma unroll
             for (int t = 0; t < M8; t++) { f[t] = f1[t]; f1[t] = f2[t]; }
-            if (bias_lane) f[M8 - 1] = rt1 - f[M8 - 1];   // b = rating - user bias (matrix.cpp:1029)
+            if (USER) {
+                const double one = (step << 2) + q < cnt ? 1.0 : 0.0;   // padding ratings are all-zero
+#pragma unroll
+                for (int s = 0; s < NS; s++) {
+                    double v = f[PLAIN + s];
+                    v = sp_one[s] ? one : v;
+                    v = sp_rating[s] ? rt1 : v;
+                    f[PLAIN + s] = v;
+                }
+            } else if (bias_lane) {
+                f[M8 - 1] = rt1 - f[M8 - 1];   // b = rating - user bias (matrix.cpp:1029)
+            }
             rt1 = rt2;
             if ((step & 7) == 0 && step > 0) {
                 ids_cur = ids_nxt;
@@ -456,7 +497,7 @@ k_gram(const GramArgs A) {
                     }
             continue;
         }
-        if (A.debug_skip_solve) {
+        if (A.debug_skip_solve & 1) {
             if (acc[0][0] == 1.2345e300) A.x[0] = acc[ST - 1][1];   // keep the accumulation alive
             continue;
         }
@@ -1072,7 +1113,8 @@ void AlsProblem::launch_half(bool user_side, cudaStream_t stream, int epilogue) 
     a.x = user_side ? uf_.p : itf_.p;
     a.partials = g.partials.p;
     a.seg_done = g.counters.p + 1;
-    a.debug_skip_solve = std::getenv("MRB_DEBUG_SKIP_SOLVE") != nullptr ? 1 : 0;
+    a.debug_skip_solve = std::getenv("MRB_DEBUG_SKIP_SOLVE") != nullptr
+                             ? std::atoi(std::getenv("MRB_DEBUG_SKIP_SOLVE")) : 0;
     a.n_peers = 0;
     const std::vector<double*>& peers = user_side ? uf_peers_ : itf_peers_;
     for (size_t j = 0; j < peers.size(); j++)
