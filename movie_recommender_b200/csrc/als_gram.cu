@@ -369,12 +369,23 @@ k_gram(const GramArgs A) {
         sp_rating[s] = USER && j == k + 1;
     }
 
+    // Dynamic scheduler, one ticket ahead: the atomic for the NEXT work item is issued before the
+    // current item's accumulation and its WorkItem is loaded before the current item's epilogue,
+    // so that neither latency is exposed between two owners (only 2 warps share a scheduler).
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(A.work_counter, 1);
+    int w = __shfl_sync(0xffffffffu, ticket, 0);
+    WorkItem wi_next{};
+    if (w < A.n_work) wi_next = A.work[w];
     for (;;) {
-        int w = 0;
-        if (lane == 0) w = atomicAdd(A.work_counter, 1);
-        w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= A.n_work) break;
-        const WorkItem wi = A.work[w];
+        const WorkItem wi = wi_next;
+        if (lane == 0) ticket = atomicAdd(A.work_counter, 1);
+        // every path to the next iteration goes through advance()
+        auto advance = [&]() {
+            w = __shfl_sync(0xffffffffu, ticket, 0);
+            if (w < A.n_work) wi_next = A.work[w];
+        };
 
         // ---------------- K1: accumulate the augmented Gram tiles ----------------
         double acc[ST][2];
@@ -390,51 +401,38 @@ k_gram(const GramArgs A) {
         double rts_cur = 0, rts_nxt = 0;
         if (lane < cnt) { ids_cur = A.other_g[wi.beg + lane]; rts_cur = A.rating_g[wi.beg + lane]; }
         if (32 + lane < cnt) { ids_nxt = A.other_g[wi.beg + 32 + lane]; rts_nxt = A.rating_g[wi.beg + 32 + lane]; }
-        auto fetch = [&](double (&dst)[M8], double& rt_out, int st, int batch_of_cur) {
-            // fragments of k-step `st` (ratings 4 st .. 4 st + 3); st's batch is the current or next
+        // prep(st): the row pointer and rating of k-step `st` (ratings 4 st .. 4 st + 3) from the
+        // id batches; st's batch is the current or the next one
+        auto prep = [&](const double*& rowp, double& rt, int st, int batch_of_cur) {
             const bool from_next = (st >> 3) != batch_of_cur;
             const int src = ((st & 7) << 2) + q;
             int id = __shfl_sync(0xffffffffu, from_next ? ids_nxt : ids_cur, src);
             if (A.debug_skip_solve & 2) id &= 15;   // measurement only: every gather hits L1
-            const double rt = shfl_double(from_next ? rts_nxt : rts_cur, src);   // 0 past the end
+            rt = shfl_double(from_next ? rts_nxt : rts_cur, src);   // 0 past the end
             const bool valid = (st << 2) + q < cnt;
             // the padding ratings of the last k-step read a row of zeros: no per-element select
-            const double* rowp = (valid ? A.other_f + static_cast<size_t>(id) * A.other_stride
-                                        : g_zero_row) + p;
+            rowp = (valid ? A.other_f + static_cast<size_t>(id) * A.other_stride : g_zero_row) + p;
+        };
+        // loads(dst, rowp): request the fragments.  Special tiles get the raw load only (or 0);
+        // the 1 / rating / rating - bias choice is made when the fragment is USED, two k-steps
+        // later: an instruction that consumes a value just requested from memory would stall
+        // the warp for the whole latency
+        auto loads = [&](double (&dst)[M8], const double* rowp) {
 #pragma unroll
             for (int t = 0; t < PLAIN; t++) dst[t] = rowp[8 * t];
-            // special tiles: the raw load only (or 0).  The 1 / rating / rating - bias choice is
-            // made when the fragment is USED, two k-steps later: an instruction that consumes a
-            // value just requested from memory would stall the warp for the whole latency
 #pragma unroll
             for (int s = 0; s < NS; s++) {
                 double v = 0.0;
                 if (sp_load[s]) v = rowp[8 * (PLAIN + s)];
                 dst[PLAIN + s] = v;
             }
-            rt_out = rt;
         };
-        double f1[M8], f2[M8], rt1 = 0, rt2 = 0;
-        fetch(f1, rt1, 0, 0);
-        fetch(f2, rt2, 1, 0);
+        const double* rowp_pend;   // pointer / rating of the next k-step to be requested
+        double rt_pend;
         const bool bias_lane = !USER && p == (k & 7);   // index k lives in the last tile (k>>3 == M8-1)
-        for (int step = 0; step < nsteps; step++) {
-            double f[M8];
-#pragma unroll
-            for (int t = 0; t < M8; t++) { f[t] = f1[t]; f1[t] = f2[t]; }
-            if (USER) {
-                const double one = (step << 2) + q < cnt ? 1.0 : 0.0;   // padding ratings are all-zero
-#pragma unroll
-                for (int s = 0; s < NS; s++) {
-                    double v = f[PLAIN + s];
-                    v = sp_one[s] ? one : v;
-                    v = sp_rating[s] ? rt1 : v;
-                    f[PLAIN + s] = v;
-                }
-            } else if (bias_lane) {
-                f[M8 - 1] = rt1 - f[M8 - 1];   // b = rating - user bias (matrix.cpp:1029)
-            }
-            rt1 = rt2;
+        // one k-step: refill the id batch, request the fragments of step + 2 into `fn`, resolve
+        // the special elements of `fu` (requested two steps ago) and issue the 28 DMMAs
+        auto kstep = [&](double (&fu)[M8], double rtu, double (&fn)[M8], double& rtn, int step) {
             if ((step & 7) == 0 && step > 0) {
                 ids_cur = ids_nxt;
                 rts_cur = rts_nxt;
@@ -443,12 +441,33 @@ k_gram(const GramArgs A) {
                 rts_nxt = 0;
                 if (e < cnt) { ids_nxt = A.other_g[wi.beg + e]; rts_nxt = A.rating_g[wi.beg + e]; }
             }
-            if (step + 2 < nsteps) fetch(f2, rt2, step + 2, step >> 3);
+            if (step + 2 < nsteps) { prep(rowp_pend, rt_pend, step + 2, step >> 3); loads(fn, rowp_pend); rtn = rt_pend; }
+            if (USER) {
+                const double one = (step << 2) + q < cnt ? 1.0 : 0.0;   // padding ratings are all-zero
+#pragma unroll
+                for (int s = 0; s < NS; s++) {
+                    double v = fu[PLAIN + s];
+                    v = sp_one[s] ? one : v;
+                    v = sp_rating[s] ? rtu : v;
+                    fu[PLAIN + s] = v;
+                }
+            } else if (bias_lane) {
+                fu[M8 - 1] = rtu - fu[M8 - 1];   // b = rating - user bias (matrix.cpp:1029)
+            }
 #pragma unroll
             for (int ti = 0; ti < M8; ti++)
 #pragma unroll
                 for (int tj = 0; tj <= ti; tj++)
-                    dmma884(acc[TI(ti, tj)][0], acc[TI(ti, tj)][1], f[ti], f[tj]);
+                    dmma884(acc[TI(ti, tj)][0], acc[TI(ti, tj)][1], fu[ti], fu[tj]);
+        };
+        // a static ring of three fragment sets (no register moves between steps)
+        double fa[M8], fb[M8], fc[M8], rta = 0, rtb = 0, rtc = 0;
+        prep(rowp_pend, rt_pend, 0, 0); loads(fa, rowp_pend); rta = rt_pend;
+        prep(rowp_pend, rt_pend, 1, 0); loads(fb, rowp_pend); rtb = rt_pend;
+        for (int step = 0; step < nsteps; step += 3) {
+            kstep(fa, rta, fc, rtc, step);
+            if (step + 1 < nsteps) kstep(fb, rtb, fa, rta, step + 1);
+            if (step + 2 < nsteps) kstep(fc, rtc, fb, rtb, step + 2);
         }
 
         // ---------------- multi-segment owners: ordered reduction by the last arriver --------
@@ -462,7 +481,7 @@ k_gram(const GramArgs A) {
             int arrived = 0;
             if (lane == 0) arrived = atomicAdd(A.seg_done + wi.multi, 1);
             arrived = __shfl_sync(0xffffffffu, arrived, 0);
-            if (arrived != wi.nseg - 1) continue;   // someone else finishes this owner
+            if (arrived != wi.nseg - 1) { advance(); continue; }   // someone else finishes this owner
             __threadfence();
 #pragma unroll
             for (int t = 0; t < ST; t++) { acc[t][0] = 0; acc[t][1] = 0; }
@@ -495,8 +514,10 @@ k_gram(const GramArgs A) {
                         }
                         if (i == n && j < n) go[j] = v;
                     }
+            advance();
             continue;
         }
+        advance();   // the next WorkItem lands while this owner is being solved
         if (A.debug_skip_solve & 1) {
             if (acc[0][0] == 1.2345e300) A.x[0] = acc[ST - 1][1];   // keep the accumulation alive
             continue;
