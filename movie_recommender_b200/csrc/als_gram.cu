@@ -35,6 +35,12 @@ namespace {
 
 constexpr int GRAM_SEG = 2048;     // ratings per work item
 constexpr int GRAM_WARPS = 4;      // warps per CTA
+#ifndef GRAM_RING_USER
+#define GRAM_RING_USER 3           // fragment sets in flight, user half-sweep (gathers hit L2)
+#endif
+#ifndef GRAM_RING_ITEM
+#define GRAM_RING_ITEM 5           // item half-sweep (the user factors spill out of L2)
+#endif
 
 struct WorkItem {
     int owner;   // row of the factor matrix being solved
@@ -358,6 +364,7 @@ k_gram(const GramArgs A) {
     // n + 1 fills the last tile, so k >= 8 (M8 - 1) - 1: every tile before the last two (users) /
     // the last one (items) is a plain load; only the NS special tiles need the per-lane choice,
     // and that choice is fixed for the whole kernel.
+    constexpr int RD = USER ? GRAM_RING_USER : GRAM_RING_ITEM;
     constexpr int PLAIN = USER ? (M8 >= 2 ? M8 - 2 : 0) : M8 - 1;
     constexpr int NS = M8 - PLAIN;
     bool sp_load[NS], sp_one[NS], sp_rating[NS];
@@ -386,6 +393,13 @@ k_gram(const GramArgs A) {
             w = __shfl_sync(0xffffffffu, ticket, 0);
             if (w < A.n_work) wi_next = A.work[w];
         };
+
+#ifndef GRAM_NO_X0_PREFETCH
+        // the owner's current factors are needed right after the accumulation (correction form
+        // of the solve): pull their cache lines into L1 now
+        if (EPI == EPI_SOLVE && lane * 16 < n)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(A.x + static_cast<size_t>(wi.owner) * n + lane * 16));
+#endif
 
         // ---------------- K1: accumulate the augmented Gram tiles ----------------
         double acc[ST][2];
@@ -441,7 +455,11 @@ k_gram(const GramArgs A) {
                 rts_nxt = 0;
                 if (e < cnt) { ids_nxt = A.other_g[wi.beg + e]; rts_nxt = A.rating_g[wi.beg + e]; }
             }
-            if (step + 2 < nsteps) { prep(rowp_pend, rt_pend, step + 2, step >> 3); loads(fn, rowp_pend); rtn = rt_pend; }
+            if (step + RD - 1 < nsteps) {
+                prep(rowp_pend, rt_pend, step + RD - 1, step >> 3);
+                loads(fn, rowp_pend);
+                rtn = rt_pend;
+            }
             if (USER) {
                 const double one = (step << 2) + q < cnt ? 1.0 : 0.0;   // padding ratings are all-zero
 #pragma unroll
@@ -460,14 +478,21 @@ k_gram(const GramArgs A) {
                 for (int tj = 0; tj <= ti; tj++)
                     dmma884(acc[TI(ti, tj)][0], acc[TI(ti, tj)][1], fu[ti], fu[tj]);
         };
-        // a static ring of three fragment sets (no register moves between steps)
-        double fa[M8], fb[M8], fc[M8], rta = 0, rtb = 0, rtc = 0;
-        prep(rowp_pend, rt_pend, 0, 0); loads(fa, rowp_pend); rta = rt_pend;
-        prep(rowp_pend, rt_pend, 1, 0); loads(fb, rowp_pend); rtb = rt_pend;
-        for (int step = 0; step < nsteps; step += 3) {
-            kstep(fa, rta, fc, rtc, step);
-            if (step + 1 < nsteps) kstep(fb, rtb, fa, rta, step + 1);
-            if (step + 2 < nsteps) kstep(fc, rtc, fb, rtb, step + 2);
+        // a static ring of RD fragment sets (no register moves between steps); fragments are
+        // requested RD - 1 k-steps before their use
+        double fr[RD][M8], rtr[RD];
+#pragma unroll
+        for (int r = 0; r < RD - 1; r++) {
+            prep(rowp_pend, rt_pend, r, 0);
+            loads(fr[r], rowp_pend);
+            rtr[r] = rt_pend;
+        }
+        rtr[RD - 1] = 0;
+        for (int step = 0; step < nsteps; step += RD) {
+#pragma unroll
+            for (int r = 0; r < RD; r++)
+                if (r == 0 || step + r < nsteps)
+                    kstep(fr[r], rtr[r], fr[(r + RD - 1) % RD], rtr[(r + RD - 1) % RD], step + r);
         }
 
         // ---------------- multi-segment owners: ordered reduction by the last arriver --------
