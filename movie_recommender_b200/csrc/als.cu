@@ -28,9 +28,12 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
     : nnz_(nnz), k_(k), nu_(num_users), ni_(num_items) {
     MRB_REQUIRE(nnz >= 0 && k >= 1 && num_users >= 0 && num_items >= 0, "als: bad sizes");
     MRB_CUDA(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
+    MRB_CUDA(cudaStreamCreateWithFlags(&s_copy_, cudaStreamNonBlocking));
+    MRB_CUDA(cudaEventCreateWithFlags(&ev_ratings_, cudaEventDisableTiming));
+    MRB_CUDA(cudaEventCreateWithFlags(&ev_factors_, cudaEventDisableTiming));
+    MRB_CUDA(cudaEventCreateWithFlags(&ev_user_done_, cudaEventDisableTiming));
+    MRB_CUDA(cudaEventCreateWithFlags(&ev_uf_copied_, cudaEventDisableTiming));
     PhaseTimer t_all("AlsProblem ctor total");
-    {
-    PhaseTimer t_alloc("  alloc + upload + id check");
     user_ids_.alloc(nnz);
     item_ids_.alloc(nnz);
     ratings_.alloc(nnz);
@@ -41,9 +44,13 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
     i_idx_.alloc(nnz);
     uf_.alloc(static_cast<size_t>(nu_) * (k + 1));
     itf_.alloc(static_cast<size_t>(ni_) * k);
+    // The ids go first on the compute stream; the ratings (half of the bytes, not needed by
+    // the grouping) follow on the copy stream while the ids are being checked and grouped.
     user_ids_.upload(user_ids, nnz, s_);
     item_ids_.upload(item_ids, nnz, s_);
-    ratings_.upload(ratings, nnz, s_);
+    ratings_.upload(ratings, nnz, s_copy_);
+    MRB_CUDA(cudaEventRecord(ev_ratings_, s_copy_));
+    ratings_pending_ = true;
 
     // ids must be zero based and inside the factor arrays (python/full_data/cpp_ls.py:120-123);
     // the reference would read out of bounds, we refuse.
@@ -56,10 +63,12 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
     int h_bad = 0;
     MRB_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s_));
     MRB_CUDA(cudaStreamSynchronize(s_));
-    MRB_REQUIRE(h_bad == 0, "als: user/item id outside [0, num_users/num_items)");
+    if (h_bad != 0) {
+        cudaStreamSynchronize(s_copy_);
+        MRB_REQUIRE(false, "als: user/item id outside [0, num_users/num_items)");
     }
-    PhaseTimer t_idx("  index build (2 group_by)");
 
+    PhaseTimer t_idx("  index build (2 group_by)");
     cudaEvent_t e0, e1;
     MRB_CUDA(cudaEventCreate(&e0));
     MRB_CUDA(cudaEventCreate(&e1));
@@ -74,19 +83,53 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
 }
 
 AlsProblem::~AlsProblem() {
+    if (s_copy_) cudaStreamSynchronize(s_copy_);
+    if (s_) cudaStreamSynchronize(s_);
     for (cudaEvent_t e : gram_events_) cudaEventDestroy(e);
     gram_events_.clear();
     gram_.reset();
+    for (cudaEvent_t e : {ev_ratings_, ev_factors_, ev_user_done_, ev_uf_copied_})
+        if (e) cudaEventDestroy(e);
+    if (s_copy_) cudaStreamDestroy(s_copy_);
     if (s_) cudaStreamDestroy(s_);
 }
 
+void AlsProblem::wait_ratings() {
+    if (!ratings_pending_) return;
+    MRB_CUDA(cudaStreamWaitEvent(s_, ev_ratings_, 0));
+    ratings_pending_ = false;
+}
+
+void AlsProblem::wait_factors() {
+    if (!factors_pending_) return;
+    MRB_CUDA(cudaStreamWaitEvent(s_, ev_factors_, 0));
+    factors_pending_ = false;
+}
+
 void AlsProblem::set_factors(const double* user_factors, const double* item_factors) {
+    wait_factors();
     uf_.upload(user_factors, uf_.n, s_);
     itf_.upload(item_factors, itf_.n, s_);
     MRB_CUDA(cudaStreamSynchronize(s_));
 }
 
+void AlsProblem::set_factors_async(const double* user_factors, const double* item_factors) {
+    // behind the ratings on the copy stream; the compute stream picks the event up when the
+    // first kernel that reads the factors is about to be enqueued (wait_factors)
+    itf_.upload(item_factors, itf_.n, s_copy_);
+    uf_.upload(user_factors, uf_.n, s_copy_);
+    MRB_CUDA(cudaEventRecord(ev_factors_, s_copy_));
+    factors_pending_ = true;
+}
+
+void AlsProblem::set_host_outputs(double* user_factors, double* item_factors) {
+    out_uf_ = user_factors;
+    out_itf_ = item_factors;
+    outputs_written_ = false;
+}
+
 void AlsProblem::get_factors(double* user_factors, double* item_factors) {
+    wait_factors();
     uf_.download(user_factors, uf_.n, s_);
     itf_.download(item_factors, itf_.n, s_);
     MRB_CUDA(cudaStreamSynchronize(s_));
@@ -117,6 +160,8 @@ AlsRunInfo AlsProblem::run(int algorithm, double min_r_decrease, int max_iterati
 AlsRunInfo AlsProblem::run_faithful(int algorithm, double min_r_decrease, int max_iteration,
                                     int T) {
     const int n = k_ + 1;
+    wait_ratings();
+    wait_factors();
     AlsFaithfulOp user_op(nnz_, nu_, user_ids_.p, item_ids_.p, u_ptr_.p, u_idx_.p, itf_.p, n, k_,
                           k_, true);
     AlsFaithfulOp item_op(nnz_, ni_, item_ids_.p, user_ids_.p, i_ptr_.p, i_idx_.p, uf_.p, k_, n,

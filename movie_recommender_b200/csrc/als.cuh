@@ -45,6 +45,16 @@ public:
     void set_factors(const double* user_factors, const double* item_factors);  // host -> device
     void get_factors(double* user_factors, double* item_factors);              // device -> host
 
+    // Pipelined host transfers for the one-shot drop-in call (als_from_python): the ratings and
+    // the initial factors ride a second stream while the ids are being grouped, and run() copies
+    // the solved user factors back while the item half-sweep is running (algorithms 3, 4).
+    // The host buffers must stay valid until run() has returned.
+    void set_factors_async(const double* user_factors, const double* item_factors);
+    void set_host_outputs(double* user_factors, double* item_factors);
+    bool outputs_written() const { return outputs_written_; }
+    // Blocks until the constructor's (and set_factors_async's) host buffers are no longer read.
+    void finish_uploads() { MRB_CUDA(cudaStreamSynchronize(s_copy_)); }
+
     // Runs the sweep loop of matrix.cpp:814-890 on the device-resident problem.
     AlsRunInfo run(int algorithm, double min_r_decrease, int max_iteration, int thread_count);
 
@@ -81,10 +91,17 @@ private:
     AlsRunInfo run_faithful(int algorithm, double min_r_decrease, int max_iteration, int T);
     AlsRunInfo run_gram(int algorithm, double min_r_decrease, int max_iteration);
     void ensure_gram();
+    void wait_ratings();   // s_ waits for the ratings upload (second stream)
+    void wait_factors();   // s_ waits for a pending set_factors_async
     void launch_half(bool user_side, cudaStream_t stream, int epilogue);
 
     int nnz_, k_, nu_, ni_;
-    cudaStream_t s_ = nullptr;
+    cudaStream_t s_ = nullptr, s_copy_ = nullptr;
+    cudaEvent_t ev_ratings_ = nullptr, ev_factors_ = nullptr, ev_user_done_ = nullptr,
+                ev_uf_copied_ = nullptr;
+    bool ratings_pending_ = false, factors_pending_ = false, outputs_written_ = false;
+    double* out_uf_ = nullptr;
+    double* out_itf_ = nullptr;
     DevBuf<int> user_ids_, item_ids_, u_ptr_, u_idx_, i_ptr_, i_idx_;
     DevBuf<double> ratings_, uf_, itf_, rmb_;
     float index_ms_ = 0;

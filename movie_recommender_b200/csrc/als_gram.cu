@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "als.cuh"
+#include "index_build.cuh"
 #include "native_cg.cuh"
 
 namespace mrb {
@@ -849,8 +850,9 @@ struct Side {
     int n_owner_items = 0;
 };
 
-void build_side(Side& sd, const int* d_ptr, const int* d_idx, const int* d_other_ids,
-                const double* d_ratings, int owners, int nnz, int rank, int world, cudaStream_t s) {
+// Grouped copies of the opposite-side ids and the ratings (what k_gram streams through).
+void build_side_gather(Side& sd, const int* d_idx, const int* d_other_ids, const double* d_ratings,
+                       int nnz, cudaStream_t s) {
     sd.other_g.alloc(nnz);
     sd.rating_g.alloc(nnz);
     if (nnz) {
@@ -859,65 +861,119 @@ void build_side(Side& sd, const int* d_ptr, const int* d_idx, const int* d_other
         MRB_LAUNCHED(1);
     }
     MRB_CUDA(cudaGetLastError());
-    std::vector<int> ptr(static_cast<size_t>(owners) + 1);
-    MRB_CUDA(cudaMemcpyAsync(ptr.data(), d_ptr, sizeof(int) * ptr.size(), cudaMemcpyDeviceToHost, s));
-    MRB_CUDA(cudaStreamSynchronize(s));
-    // this rank's contiguous, nnz-balanced owner range
-    std::vector<int> bounds(static_cast<size_t>(world) + 1);
-    balanced_ranges(ptr.data(), owners, world, bounds.data());
-    sd.lo = bounds[rank];
-    sd.hi = bounds[rank + 1];
-    // longest-processing-time-first order: owners by descending degree (stable)
-    // (counting sort by degree: stable, O(owners + max degree))
-    std::vector<int> order(static_cast<size_t>(sd.hi - sd.lo));
-    {
-        int max_deg = 0;
-        for (int o = sd.lo; o < sd.hi; o++) max_deg = std::max(max_deg, ptr[o + 1] - ptr[o]);
-        std::vector<int> start(static_cast<size_t>(max_deg) + 2, 0);
-        for (int o = sd.lo; o < sd.hi; o++) start[max_deg - (ptr[o + 1] - ptr[o]) + 1]++;
-        for (int d = 0; d <= max_deg; d++) start[d + 1] += start[d];
-        for (int o = sd.lo; o < sd.hi; o++) order[start[max_deg - (ptr[o + 1] - ptr[o])]++] = o;
+}
+
+// ---- work lists, built on the device --------------------------------------------------------
+// Owners of this rank's range in longest-processing-time-first order (degree descending, stable;
+// degrees above 65534 share the first bucket), every owner cut into segments of GRAM_SEG ratings.
+constexpr int LPT_KEYS = 65536;
+
+__global__ void k_lpt_keys(const int* __restrict__ ptr, int lo, int m, int* __restrict__ key) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int deg = ptr[lo + i + 1] - ptr[lo + i];
+    key[i] = deg >= LPT_KEYS - 1 ? 0 : LPT_KEYS - 1 - deg;
+}
+
+// per owner in LPT order: work items, multi-segment flag, partial-tile slots, non-empty flag
+// (entry m of each array is 0, so that the exclusive scans leave the totals there)
+__global__ void k_owner_counts(const int* __restrict__ ptr, int lo, int m,
+                               const int* __restrict__ order, int* __restrict__ n_items,
+                               int* __restrict__ is_multi, int* __restrict__ n_slots,
+                               int* __restrict__ nonempty) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > m) return;
+    int nseg = 0;
+    if (j < m) {
+        const int o = lo + order[j];
+        const int deg = ptr[o + 1] - ptr[o];
+        nseg = (deg + GRAM_SEG - 1) / GRAM_SEG;
     }
-    std::vector<WorkItem> work;
-    work.reserve(order.size() + nnz / GRAM_SEG + 1);
-    sd.n_multi = 0;
-    sd.n_slots = 0;
-    for (int o : order) {
-        const int beg = ptr[o], end = ptr[o + 1];
-        const int deg = end - beg;
-        if (deg == 0) continue;  // no equations: the factors keep their previous value
-        const int nseg = deg <= GRAM_SEG ? 1 : (deg + GRAM_SEG - 1) / GRAM_SEG;
-        for (int sg = 0; sg < nseg; sg++) {
-            WorkItem wi;
-            wi.owner = o;
-            wi.beg = beg + sg * GRAM_SEG;
-            wi.end = std::min(end, wi.beg + GRAM_SEG);
-            wi.seg = sg;
-            wi.nseg = nseg;
-            wi.slot = nseg > 1 ? sd.n_slots : 0;
-            wi.multi = nseg > 1 ? sd.n_multi : -1;
-            wi.pad = 0;
-            work.push_back(wi);
-        }
-        if (nseg > 1) { sd.n_multi++; sd.n_slots += nseg; }
+    n_items[j] = nseg;
+    is_multi[j] = nseg > 1;
+    n_slots[j] = nseg > 1 ? nseg : 0;
+    nonempty[j] = nseg > 0;
+}
+
+__global__ void k_write_work(const int* __restrict__ ptr, int lo, int m,
+                             const int* __restrict__ order, const int* __restrict__ item_at,
+                             const int* __restrict__ multi_at, const int* __restrict__ slot_at,
+                             const int* __restrict__ nonempty_at, WorkItem* __restrict__ work,
+                             int* __restrict__ owner_order) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const int o = lo + order[j];
+    const int beg = ptr[o], end = ptr[o + 1];
+    const int nseg = item_at[j + 1] - item_at[j];
+    if (nseg == 0) return;   // no equations: the factors keep their previous value
+    owner_order[nonempty_at[j]] = o;
+    for (int sg = 0; sg < nseg; sg++) {
+        WorkItem wi;
+        wi.owner = o;
+        wi.beg = beg + sg * GRAM_SEG;
+        wi.end = min(end, wi.beg + GRAM_SEG);
+        wi.seg = sg;
+        wi.nseg = nseg;
+        wi.slot = nseg > 1 ? slot_at[j] : 0;
+        wi.multi = nseg > 1 ? multi_at[j] : -1;
+        wi.pad = 0;
+        work[item_at[j] + sg] = wi;
     }
-    {
-        std::vector<int> nonempty;
-        nonempty.reserve(order.size());
-        for (int o : order)
-            if (ptr[o + 1] > ptr[o]) nonempty.push_back(o);
-        sd.n_owner_items = static_cast<int>(nonempty.size());
-        sd.owner_order.alloc(std::max<size_t>(nonempty.size(), 1));
-        if (!nonempty.empty())
-            MRB_CUDA(cudaMemcpyAsync(sd.owner_order.p, nonempty.data(), sizeof(int) * nonempty.size(),
-                                     cudaMemcpyHostToDevice, s));
+}
+
+// This rank's owner range and its work lists.  Needs the CSR pointers only, so it is enqueued
+// while the ratings are still on their way to the device.  Host round trips: the pointer array
+// when the rows are sharded (the balanced ranges are a host decision every rank must agree on),
+// and four totals.
+void build_side_lists(Side& sd, const int* d_ptr, int owners, int nnz, int rank, int world,
+                      cudaStream_t s) {
+    PhaseTimer t2("  side: work lists");
+    sd.lo = 0;
+    sd.hi = owners;
+    if (world > 1) {
+        std::vector<int> ptr(static_cast<size_t>(owners) + 1);
+        MRB_CUDA(cudaMemcpyAsync(ptr.data(), d_ptr, sizeof(int) * ptr.size(), cudaMemcpyDeviceToHost, s));
         MRB_CUDA(cudaStreamSynchronize(s));
+        std::vector<int> bounds(static_cast<size_t>(world) + 1);
+        balanced_ranges(ptr.data(), owners, world, bounds.data());
+        sd.lo = bounds[rank];
+        sd.hi = bounds[rank + 1];
     }
-    sd.n_work = static_cast<int>(work.size());
-    sd.work.alloc(work.size());
-    MRB_CUDA(cudaMemcpyAsync(sd.work.p, work.data(), sizeof(WorkItem) * work.size(),
-                             cudaMemcpyHostToDevice, s));
-    MRB_CUDA(cudaStreamSynchronize(s));
+    const int m = sd.hi - sd.lo;
+    sd.n_work = sd.n_multi = sd.n_slots = sd.n_owner_items = 0;
+    sd.owner_order.alloc(static_cast<size_t>(std::max(m, 1)));
+    // every owner has at most deg / GRAM_SEG + 1 items
+    sd.work.alloc(static_cast<size_t>(m) + static_cast<size_t>(nnz) / GRAM_SEG + 1);
+    if (m == 0) return;
+    DevBuf<int> key(m), kptr(LPT_KEYS + 1), order(m);
+    DevBuf<int> counts(4 * (static_cast<size_t>(m) + 1));
+    int* item_at = counts.p;
+    int* multi_at = item_at + m + 1;
+    int* slot_at = multi_at + m + 1;
+    int* nonempty_at = slot_at + m + 1;
+    k_lpt_keys<<<ceil_div(m, 256), 256, 0, s>>>(d_ptr, sd.lo, m, key.p);
+    MRB_LAUNCHED(1);
+    stable_group_by(key.p, m, LPT_KEYS, kptr.p, order.p, s);
+    k_owner_counts<<<ceil_div(m + 1, 256), 256, 0, s>>>(d_ptr, sd.lo, m, order.p, item_at, multi_at,
+                                                       slot_at, nonempty_at);
+    MRB_LAUNCHED(1);
+    exclusive_scan_i32(item_at, item_at, m + 1, s);
+    exclusive_scan_i32(multi_at, multi_at, m + 1, s);
+    exclusive_scan_i32(slot_at, slot_at, m + 1, s);
+    exclusive_scan_i32(nonempty_at, nonempty_at, m + 1, s);
+    k_write_work<<<ceil_div(m, 256), 256, 0, s>>>(d_ptr, sd.lo, m, order.p, item_at, multi_at,
+                                                 slot_at, nonempty_at, sd.work.p, sd.owner_order.p);
+    MRB_LAUNCHED(1);
+    MRB_CUDA(cudaGetLastError());
+    int totals[4] = {0, 0, 0, 0};
+    for (int t = 0; t < 4; t++)
+        MRB_CUDA(cudaMemcpyAsync(&totals[t], counts.p + static_cast<size_t>(t) * (m + 1) + m,
+                                 sizeof(int), cudaMemcpyDeviceToHost, s));
+    MRB_CUDA(cudaStreamSynchronize(s));   // also: the scratch buffers are released on return
+    sd.n_work = totals[0];
+    sd.n_multi = totals[1];
+    sd.n_slots = totals[2];
+    sd.n_owner_items = totals[3];
 }
 
 template <int M8, bool USER, int EPI>
@@ -1032,8 +1088,11 @@ void AlsProblem::ensure_gram() {
     int dev = 0;
     MRB_CUDA(cudaGetDevice(&dev));
     MRB_CUDA(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, dev));
-    build_side(g.user, u_ptr_.p, u_idx_.p, item_ids_.p, ratings_.p, nu_, nnz_, rank_, world_, s_);
-    build_side(g.item, i_ptr_.p, i_idx_.p, user_ids_.p, ratings_.p, ni_, nnz_, rank_, world_, s_);
+    build_side_lists(g.user, u_ptr_.p, nu_, nnz_, rank_, world_, s_);
+    build_side_lists(g.item, i_ptr_.p, ni_, nnz_, rank_, world_, s_);
+    wait_ratings();
+    build_side_gather(g.user, u_idx_.p, item_ids_.p, ratings_.p, nnz_, s_);
+    build_side_gather(g.item, i_idx_.p, user_ids_.p, ratings_.p, nnz_, s_);
     g.wide = m8 > 7;
     g.st_doubles = g.wide ? 1 : m8 * (m8 + 1) / 2 * 64;
     const int slots = g.wide ? 1 : std::max(g.user.n_slots, g.item.n_slots);
@@ -1272,10 +1331,22 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
         g.cg_partials.alloc(static_cast<size_t>(ceil_div(static_cast<long long>(len), 256)) + 1);
         g.cg_state.alloc(1);
     }
+    wait_factors();
+    // the solved user factors travel to the host while the item half-sweep runs
+    auto copy_user_factors_out = [&]() {
+        if (out_uf_ == nullptr) return;
+        MRB_CUDA(cudaEventRecord(ev_user_done_, s_));
+        MRB_CUDA(cudaStreamWaitEvent(s_copy_, ev_user_done_, 0));
+        uf_.download(out_uf_, uf_.n, s_copy_);
+        MRB_CUDA(cudaEventRecord(ev_uf_copied_, s_copy_));
+    };
+    bool uf_copy_in_flight = false;
     while (sweep < max_iteration) {
         double rr = 0;
+        if (uf_copy_in_flight) MRB_CUDA(cudaStreamWaitEvent(s_, ev_uf_copied_, 0));
         if (algorithm == ALS_GRAM_CHOLESKY) {
             launch_half(true, s_, EPI_SOLVE);
+            copy_user_factors_out();
             launch_half(false, s_, EPI_SOLVE);
             // rr := sum of squared training errors (the exact solve leaves no normal-equation
             // residual to monitor); same relative-decrease rule as matrix.cpp:871-875.
@@ -1285,11 +1356,13 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
             // als(), matrix.cpp:818, 854-855) with global alpha/beta over all owners
             launch_half(true, s_, EPI_STORE);
             CgResult ur = block_cg_solve(g, uf_.p, nu_, k_ + 1, s_);
+            copy_user_factors_out();
             launch_half(false, s_, EPI_STORE);
             CgResult ir = block_cg_solve(g, itf_.p, ni_, k_, s_);
             info.cg_iterations += ur.iterations + ir.iterations;
             rr = ir.final_rr;
         }
+        uf_copy_in_flight = out_uf_ != nullptr;
         info.sweeps_run++;
         info.last_rr = rr;
         if (sweep >= 3) {
@@ -1300,6 +1373,11 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
         sweep++;
     }
     info.sweeps_returned = sweep;
+    if (out_itf_ != nullptr && info.sweeps_run > 0) {
+        itf_.download(out_itf_, itf_.n, s_);
+        MRB_CUDA(cudaStreamSynchronize(s_copy_));
+        outputs_written_ = true;
+    }
     MRB_CUDA(cudaStreamSynchronize(s_));
     info.gram_ms = collect_gram_ms();
     return info;

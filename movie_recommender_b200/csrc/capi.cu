@@ -121,17 +121,18 @@ int als_from_python(int* user_ids, int* item_ids, int ratings_length, double* ra
         PhaseTimer t_all("als_from_python total");
         AlsProblem p(user_ids, item_ids, ratings_length, ratings_values, k,
                      user_factors_length / (k + 1), item_factors_length / k);
-        {
-            PhaseTimer t("set_factors");
-            p.set_factors(user_factors_values, item_factors_values);
-        }
+        // The factor buffers are in/out and outlive this call: their upload rides the copy stream
+        // behind the ratings, and algorithms 3/4 copy the results back from inside the sweep loop.
+        p.set_factors_async(user_factors_values, item_factors_values);
+        if (algorithm == ALS_GRAM_CG || algorithm == ALS_GRAM_CHOLESKY)
+            p.set_host_outputs(user_factors_values, item_factors_values);
         AlsRunInfo info;
         {
             PhaseTimer t("run");
             info = p.run(algorithm, min_r_decrease, max_iteration, g_thread_count);
         }
         PhaseTimer t("get_factors + teardown");
-        p.get_factors(user_factors_values, item_factors_values);
+        if (!p.outputs_written()) p.get_factors(user_factors_values, item_factors_values);
         return info.sweeps_returned;
     });
 }
@@ -240,6 +241,7 @@ int mrb_als_create(const int* user_ids, const int* item_ids, int num_ratings,
         MRB_REQUIRE(out != nullptr, "mrb_als_create: null out");
         *out = new mrb_als_problem(user_ids, item_ids, num_ratings, ratings, num_item_factors,
                                    num_users, num_items);
+        (*out)->impl.finish_uploads();   // the caller may release its arrays once this returns
         return 0;
     });
 }
