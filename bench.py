@@ -326,7 +326,8 @@ def main():
         for key in ("user_ids", "item_ids", "ratings", "user_factors0", "item_factors0"):
             pinned[key], t = pinned_copy(p[key])
             keep_alive.append(t)
-        e2e_s_multi, _, _ = _sh.e2e_steps(pinned, k, nu, ni, rank, world, max(1, min(args.e2e_steps, 3)))
+        e2e_s_multi, _, _ = _sh.e2e_steps(pinned, k, nu, ni, rank, world, max(1, min(args.e2e_steps, 3)),
+                                           timing=bool(os.environ.get("MRB_E2E_TIMING")))
     value = nnz / (step_ms * 1e-3)
 
     if rank != 0:

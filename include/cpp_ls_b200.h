@@ -138,6 +138,13 @@ MRB_API int mrb_als_create(const int* user_ids, const int* item_ids, int num_rat
                    const double* ratings, int num_item_factors, int num_users, int num_items,
                    mrb_als_problem** out);
 MRB_API int mrb_als_set_factors(mrb_als_problem* p, const double* user_factors, const double* item_factors);
+/* Same upload, enqueued on the problem's copy stream without waiting: every later call on the
+ * problem is ordered after it.  The two host arrays must stay valid (and unmodified) until a
+ * later mrb_als_run / mrb_als_get_factors / mrb_als_shard_sse on this problem has returned. */
+MRB_API int mrb_als_set_factors_async(mrb_als_problem* p, const double* user_factors, const double* item_factors);
+/* Blocks until every upload enqueued by mrb_als_create / mrb_als_set_factors_async has landed
+ * (multi-GPU: call it before the barrier after which peers may store into this rank's replicas). */
+MRB_API int mrb_als_finish_uploads(mrb_als_problem* p);
 MRB_API int mrb_als_get_factors(mrb_als_problem* p, double* user_factors, double* item_factors);
 /* Copies out the two groupings (u_ptr[num_users+1], u_idx[nnz], i_ptr[num_items+1], i_idx[nnz]). */
 MRB_API int mrb_als_get_index(mrb_als_problem* p, int* u_ptr, int* u_idx, int* i_ptr, int* i_idx);

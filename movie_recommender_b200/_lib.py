@@ -73,6 +73,10 @@ def _declare(dll):
                                    ctypes.POINTER(c_void_p)]
     dll.mrb_als_set_factors.restype = c_int
     dll.mrb_als_set_factors.argtypes = [c_void_p, _D, _D]
+    dll.mrb_als_finish_uploads.restype = c_int
+    dll.mrb_als_finish_uploads.argtypes = [c_void_p]
+    dll.mrb_als_set_factors_async.restype = c_int
+    dll.mrb_als_set_factors_async.argtypes = [c_void_p, _D, _D]
     dll.mrb_als_get_factors.restype = c_int
     dll.mrb_als_get_factors.argtypes = [c_void_p, _D, _D]
     dll.mrb_als_get_index.restype = c_int

@@ -180,16 +180,34 @@ class AlsProblem:
     def __exit__(self, *exc):
         self.close()
 
-    def set_factors(self, user_factors, item_factors):
+    def set_factors(self, user_factors, item_factors, wait=True):
+        """Host -> device.  wait=False enqueues the upload on the problem's copy stream and
+        returns at once (page-locked arrays only make that asynchronous); the arrays are kept
+        referenced by this object and must not be modified until the next run / get_factors."""
         uf = numpy.ascontiguousarray(user_factors, dtype=numpy.double).reshape(-1)
         itf = numpy.ascontiguousarray(item_factors, dtype=numpy.double).reshape(-1)
         assert len(uf) == self.num_users * (self.k + 1) and len(itf) == self.num_items * self.k
-        _lib.check(_dll.mrb_als_set_factors(self._h, _lib.dp(uf), _lib.dp(itf)))
+        if wait:
+            _lib.check(_dll.mrb_als_set_factors(self._h, _lib.dp(uf), _lib.dp(itf)))
+        else:
+            self._pending_factors = (uf, itf)
+            _lib.check(_dll.mrb_als_set_factors_async(self._h, _lib.dp(uf), _lib.dp(itf)))
 
-    def get_factors(self):
-        uf = numpy.empty(self.num_users * (self.k + 1), dtype=numpy.double)
-        itf = numpy.empty(self.num_items * self.k, dtype=numpy.double)
-        _lib.check(_dll.mrb_als_get_factors(self._h, _lib.dp(uf), _lib.dp(itf)))
+    def finish_uploads(self):
+        """Blocks until the uploads enqueued by the constructor / set_factors(wait=False) landed."""
+        _lib.check(_dll.mrb_als_finish_uploads(self._h))
+        self._pending_factors = None
+
+    def get_factors(self, out_user_factors=None, out_item_factors=None):
+        """Device -> host.  With `out_*` (flat, contiguous float64 arrays of the right length,
+        e.g. page-locked buffers) the factors are written in place and those arrays returned."""
+        nu, ni = self.num_users * (self.k + 1), self.num_items * self.k
+        uf = numpy.empty(nu, dtype=numpy.double) if out_user_factors is None else out_user_factors
+        itf = numpy.empty(ni, dtype=numpy.double) if out_item_factors is None else out_item_factors
+        for a, n in ((uf, nu), (itf, ni)):
+            if a.dtype != numpy.double or not a.flags.c_contiguous or a.size != n:
+                raise ValueError("get_factors: out arrays must be contiguous float64 of the factor length")
+        _lib.check(_dll.mrb_als_get_factors(self._h, _lib.dp(uf.reshape(-1)), _lib.dp(itf.reshape(-1))))
         return uf, itf
 
     def get_factors_synced(self):

@@ -33,6 +33,7 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
     MRB_CUDA(cudaEventCreateWithFlags(&ev_factors_, cudaEventDisableTiming));
     MRB_CUDA(cudaEventCreateWithFlags(&ev_user_done_, cudaEventDisableTiming));
     MRB_CUDA(cudaEventCreateWithFlags(&ev_uf_copied_, cudaEventDisableTiming));
+    MRB_CUDA(cudaEventCreateWithFlags(&ev_prepared_, cudaEventDisableTiming));
     PhaseTimer t_all("AlsProblem ctor total");
     user_ids_.alloc(nnz);
     item_ids_.alloc(nnz);
@@ -88,7 +89,7 @@ AlsProblem::~AlsProblem() {
     for (cudaEvent_t e : gram_events_) cudaEventDestroy(e);
     gram_events_.clear();
     gram_.reset();
-    for (cudaEvent_t e : {ev_ratings_, ev_factors_, ev_user_done_, ev_uf_copied_})
+    for (cudaEvent_t e : {ev_ratings_, ev_factors_, ev_user_done_, ev_uf_copied_, ev_prepared_})
         if (e) cudaEventDestroy(e);
     if (s_copy_) cudaStreamDestroy(s_copy_);
     if (s_) cudaStreamDestroy(s_);
@@ -106,6 +107,16 @@ void AlsProblem::wait_factors() {
     factors_pending_ = false;
 }
 
+void AlsProblem::order_after_inputs(cudaStream_t stream) {
+    if (stream == s_) {
+        wait_factors();
+        return;   // s_ is ordered after its own work; the ratings were awaited by ensure_gram
+    }
+    MRB_CUDA(cudaStreamWaitEvent(stream, ev_ratings_, 0));
+    if (factors_recorded_) MRB_CUDA(cudaStreamWaitEvent(stream, ev_factors_, 0));
+    if (prepared_recorded_) MRB_CUDA(cudaStreamWaitEvent(stream, ev_prepared_, 0));
+}
+
 void AlsProblem::set_factors(const double* user_factors, const double* item_factors) {
     wait_factors();
     uf_.upload(user_factors, uf_.n, s_);
@@ -120,6 +131,7 @@ void AlsProblem::set_factors_async(const double* user_factors, const double* ite
     uf_.upload(user_factors, uf_.n, s_copy_);
     MRB_CUDA(cudaEventRecord(ev_factors_, s_copy_));
     factors_pending_ = true;
+    factors_recorded_ = true;
 }
 
 void AlsProblem::set_host_outputs(double* user_factors, double* item_factors) {

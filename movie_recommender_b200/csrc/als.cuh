@@ -93,13 +93,17 @@ private:
     void ensure_gram();
     void wait_ratings();   // s_ waits for the ratings upload (second stream)
     void wait_factors();   // s_ waits for a pending set_factors_async
+    // A caller-provided stream (half_sweep, shard_sse) waits for everything this object has put
+    // on its own streams: the uploads and the grouped copies made by ensure_gram.
+    void order_after_inputs(cudaStream_t stream);
     void launch_half(bool user_side, cudaStream_t stream, int epilogue);
 
     int nnz_, k_, nu_, ni_;
     cudaStream_t s_ = nullptr, s_copy_ = nullptr;
     cudaEvent_t ev_ratings_ = nullptr, ev_factors_ = nullptr, ev_user_done_ = nullptr,
-                ev_uf_copied_ = nullptr;
+                ev_uf_copied_ = nullptr, ev_prepared_ = nullptr;
     bool ratings_pending_ = false, factors_pending_ = false, outputs_written_ = false;
+    bool factors_recorded_ = false, prepared_recorded_ = false;
     double* out_uf_ = nullptr;
     double* out_itf_ = nullptr;
     DevBuf<int> user_ids_, item_ids_, u_ptr_, u_idx_, i_ptr_, i_idx_;

@@ -445,8 +445,8 @@ k_gram(const GramArgs A) {
         const double* rowp_pend;   // pointer / rating of the next k-step to be requested
         double rt_pend;
         const bool bias_lane = !USER && p == (k & 7);   // index k lives in the last tile (k>>3 == M8-1)
-        // one k-step: refill the id batch, request the fragments of step + 2 into `fn`, resolve
-        // the special elements of `fu` (requested two steps ago) and issue the 28 DMMAs
+        // one k-step: refill the id batch, request the fragments of step + RD - 1 into `fn`,
+        // resolve the special elements of `fu` (requested RD - 1 steps ago), issue the 28 DMMAs
         auto kstep = [&](double (&fu)[M8], double rtu, double (&fn)[M8], double& rtn, int step) {
             if ((step & 7) == 0 && step > 0) {
                 ids_cur = ids_nxt;
@@ -1093,6 +1093,8 @@ void AlsProblem::ensure_gram() {
     wait_ratings();
     build_side_gather(g.user, u_idx_.p, item_ids_.p, ratings_.p, nnz_, s_);
     build_side_gather(g.item, i_idx_.p, user_ids_.p, ratings_.p, nnz_, s_);
+    MRB_CUDA(cudaEventRecord(ev_prepared_, s_));
+    prepared_recorded_ = true;
     g.wide = m8 > 7;
     g.st_doubles = g.wide ? 1 : m8 * (m8 + 1) / 2 * 64;
     const int slots = g.wide ? 1 : std::max(g.user.n_slots, g.item.n_slots);
@@ -1290,11 +1292,13 @@ void AlsProblem::set_peers(const std::vector<double*>& user_factor_peers,
 
 void AlsProblem::half_sweep(bool user_side, cudaStream_t stream) {
     ensure_gram();
+    order_after_inputs(stream);
     launch_half(user_side, stream, EPI_SOLVE);
 }
 
 double AlsProblem::shard_sse(cudaStream_t stream) {
     ensure_gram();
+    order_after_inputs(stream);
     GramState& g = *gram_;
     k_sum_fixed<<<1, 1024, 0, stream>>>(g.sse_owner.p, ni_, g.sse_partials.p);
     MRB_LAUNCHED(1);

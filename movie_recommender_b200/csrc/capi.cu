@@ -5,6 +5,10 @@
 #include <memory>
 #include <vector>
 
+#include <map>
+#include <mutex>
+#include <string>
+
 #include "als.cuh"
 #include "common.cuh"
 #include "faithful_cg.cuh"
@@ -226,11 +230,11 @@ int mrb_csr_transpose(int rows, int cols, const int* rowptr, const int* colidx, 
 
 struct mrb_als_problem {
     AlsProblem impl;
-    std::vector<void*> opened;   // cudaIpcOpenMemHandle mappings to close
+    // (peer mappings live in g_ipc_cache, not here: they outlive the problem)
     mrb_als_problem(const int* u, const int* i, int nnz, const double* r, int k, int nu, int ni)
         : impl(u, i, nnz, r, k, nu, ni) {}
     ~mrb_als_problem() {
-        for (void* q : opened) cudaIpcCloseMemHandle(q);
+
     }
 };
 
@@ -250,6 +254,23 @@ int mrb_als_set_factors(mrb_als_problem* p, const double* user_factors, const do
     return guarded([&] {
         MRB_REQUIRE(p != nullptr, "null problem");
         p->impl.set_factors(user_factors, item_factors);
+        return 0;
+    });
+}
+
+int mrb_als_set_factors_async(mrb_als_problem* p, const double* user_factors,
+                              const double* item_factors) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        p->impl.set_factors_async(user_factors, item_factors);
+        return 0;
+    });
+}
+
+int mrb_als_finish_uploads(mrb_als_problem* p) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        p->impl.finish_uploads();
         return 0;
     });
 }
@@ -349,6 +370,31 @@ int mrb_als_ipc_handles(mrb_als_problem* p, unsigned char* user_handle64,
     });
 }
 
+// Peer mappings are cached by handle for the life of the process (closed by mrb_trim_memory):
+// the arena hands a re-created problem the same device blocks, so a training loop that builds
+// one problem per step opens every peer buffer once (cudaIpcOpenMemHandle costs milliseconds).
+static std::mutex g_ipc_mutex;
+static std::map<std::string, void*> g_ipc_cache;
+
+static void* ipc_open_cached(const unsigned char* handle64) {
+    std::lock_guard<std::mutex> lock(g_ipc_mutex);
+    const std::string key(reinterpret_cast<const char*>(handle64), 64);
+    auto it = g_ipc_cache.find(key);
+    if (it != g_ipc_cache.end()) return it->second;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    void* q = nullptr;
+    MRB_CUDA(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+    g_ipc_cache.emplace(key, q);
+    return q;
+}
+
+static void ipc_close_all() {
+    std::lock_guard<std::mutex> lock(g_ipc_mutex);
+    for (auto& kv : g_ipc_cache) cudaIpcCloseMemHandle(kv.second);
+    g_ipc_cache.clear();
+}
+
 int mrb_als_open_peers(mrb_als_problem* p, const unsigned char* user_handles,
                        const unsigned char* item_handles, int world, int rank) {
     return guarded([&] {
@@ -361,16 +407,8 @@ int mrb_als_open_peers(mrb_als_problem* p, const unsigned char* user_handles,
                 ip[r] = p->impl.item_factors();
                 continue;
             }
-            cudaIpcMemHandle_t hu, hi;
-            std::memcpy(&hu, user_handles + 64 * r, 64);
-            std::memcpy(&hi, item_handles + 64 * r, 64);
-            void* q = nullptr;
-            MRB_CUDA(cudaIpcOpenMemHandle(&q, hu, cudaIpcMemLazyEnablePeerAccess));
-            p->opened.push_back(q);
-            up[r] = static_cast<double*>(q);
-            MRB_CUDA(cudaIpcOpenMemHandle(&q, hi, cudaIpcMemLazyEnablePeerAccess));
-            p->opened.push_back(q);
-            ip[r] = static_cast<double*>(q);
+            up[r] = static_cast<double*>(ipc_open_cached(user_handles + 64 * r));
+            ip[r] = static_cast<double*>(ipc_open_cached(item_handles + 64 * r));
         }
         p->impl.set_peers(up, ip);
         return 0;
@@ -417,7 +455,10 @@ int mrb_als_collect_gram_ms(mrb_als_problem* p, float* out) {
 
 long long mrb_kernel_launches(void) { return g_kernel_launches.load(); }
 
-void mrb_trim_memory(void) { arena_trim(); }
+void mrb_trim_memory(void) {
+    ipc_close_all();
+    arena_trim();
+}
 
 struct mrb_cosim {
     Cosim impl;

@@ -28,7 +28,8 @@ class _DevArray:
 
 
 class ShardedAls:
-    def __init__(self, problem, k, num_users, num_items, rank, world, exchange="p2p"):
+    def __init__(self, problem, k, num_users, num_items, rank, world, exchange="p2p",
+                 async_upload=False):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -36,16 +37,27 @@ class ShardedAls:
         self.nu, self.ni = num_users, num_items
         self.exchange = exchange
         self.nnz = len(problem["ratings"])
+        import os
+        import time
+        marks = [("start", time.time())]
         self.prob = cpp_ls.AlsProblem(problem["user_ids"], problem["item_ids"], problem["ratings"],
                                       k, num_users, num_items)
-        self.prob.set_factors(problem["user_factors0"], problem["item_factors0"])
+        marks.append(("problem", time.time()))
+        # async_upload: the factors ride the copy stream behind the ratings (the caller keeps
+        # problem["*_factors0"] alive and untouched until the first get_factors)
+        self.prob.set_factors(problem["user_factors0"], problem["item_factors0"],
+                              wait=not async_upload)
+        marks.append(("set_factors", time.time()))
         self.ranges = self.prob.set_shard(rank, world)
+        marks.append(("set_shard", time.time()))
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.flag = torch.zeros(1, device=self.device)
         if exchange == "p2p":
             handles = [None] * world
             dist.all_gather_object(handles, self.prob.ipc_handles())
+            marks.append(("handle exchange", time.time()))
             self.prob.open_peers([h[0] for h in handles], [h[1] for h in handles], rank)
+            marks.append(("open_peers", time.time()))
         else:
             pu, pi = self.prob.device_factors()
             self.uf = torch.as_tensor(_DevArray(pu, num_users * (k + 1)), device=self.device)
@@ -54,7 +66,15 @@ class ShardedAls:
             dist.all_gather_object(all_ranges, self.ranges)
             self.u_views = [self.uf[r[0] * (k + 1):r[1] * (k + 1)] for r in all_ranges]
             self.i_views = [self.itf[r[2] * k:r[3] * k] for r in all_ranges]
+        # past the barrier the peers may store solved rows into this rank's replicas: its own
+        # (possibly still running) factor upload must have landed before that
+        self.prob.finish_uploads()
         dist.barrier()
+        marks.append(("barrier", time.time()))
+        if rank == 0 and os.environ.get("MRB_E2E_TIMING"):
+            import sys
+            print("[ShardedAls] " + ", ".join("%s %.1f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3)
+                                              for i in range(1, len(marks))), file=sys.stderr)
 
     def _exchange(self, user_side):
         if self.exchange == "p2p":
@@ -129,30 +149,39 @@ class ShardedAls:
                     sse=sse, exchange=self.exchange, ranges=self.ranges)
 
 
-def e2e_steps(problem, k, num_users, num_items, rank, world, steps, exchange="p2p"):
+def e2e_steps(problem, k, num_users, num_items, rank, world, steps, exchange="p2p", timing=False):
     """End-to-end time of one sharded sweep from HOST buffers, per step: every rank uploads the
-    (page-locked) ratings and factors, builds its indices and work lists, exchanges the peer
-    mappings, runs one sweep and copies the factors back.  Returns seconds per step (max over
-    ranks) and the factors of the last step."""
+    ratings and factors, builds its indices and work lists, maps the peers' factor buffers, runs
+    one sweep and copies the factors back INTO `problem["user_factors0"/"item_factors0"]` (pass
+    page-locked arrays: a pageable 137 MB copy each way costs more than the sweep).  Returns
+    seconds per step (max over ranks) and the factor arrays."""
     import time
 
     import torch
     import torch.distributed as dist
-    cur = dict(problem)
     times = []
+    uf_host = problem["user_factors0"].reshape(-1)
+    itf_host = problem["item_factors0"].reshape(-1)
     for step in range(steps + 1):              # step 0 is a warm-up
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.time()
-        s = ShardedAls(cur, k, num_users, num_items, rank, world, exchange=exchange)
+        s = ShardedAls(problem, k, num_users, num_items, rank, world, exchange=exchange,
+                       async_upload=True)
+        t1 = time.time()
         s.sweep()
         torch.cuda.synchronize()
         dist.barrier()
-        uf, itf = s.prob.get_factors()
-        dt = torch.tensor([time.time() - t0], dtype=torch.float64, device=s.device)
+        t2 = time.time()
+        s.prob.get_factors(uf_host, itf_host)
+        t3 = time.time()
+        dt = torch.tensor([t3 - t0], dtype=torch.float64, device=s.device)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         s.prob.close()
-        cur["user_factors0"], cur["item_factors0"] = uf, itf
+        if timing and rank == 0:
+            import sys
+            print("[e2e N=%d step %d] setup %.1f ms, sweep+barrier %.1f ms, get_factors %.1f ms" % (
+                world, step, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3), file=sys.stderr)
         if step > 0:
             times.append(float(dt.item()))
-    return sum(times) / len(times), cur["user_factors0"], cur["item_factors0"]
+    return sum(times) / len(times), uf_host, itf_host
