@@ -46,9 +46,9 @@ WORKLOAD = dict(name="C3: ALS rank 50, ML-27M shape", num_users=283228, num_item
                 num_ratings=27753444, k=50)
 FP64_DMMA_PEAK_TFLOPS = 37.09   # measured on this pool's B200 with tools/fp64_peak.cu (profiles/)
 # dram__bytes_read.sum + dram__bytes_write.sum of the two k_gram launches of one sweep at C3 from
-# the ncu --set full capture profiles/ncu_k_gram_C3_r01_v3.txt (user side 0.67 GB, movie side
-# 3.87 GB): far BELOW the algorithmic gather bytes because the factor rows are served by L2.
-NCU_DRAM_BYTES_PER_LAUNCH_C3 = (0.557721e9 + 0.115088e9 + 3.756290e9 + 0.114815e9) / 2.0
+# the ncu --set full capture profiles/ncu_k_gram_C3_r01_v4.txt (user side 0.67 GB, movie side
+# 4.17 GB): far BELOW the algorithmic gather bytes because the factor rows are served by L2.
+NCU_DRAM_BYTES_PER_LAUNCH_C3 = (0.558801e9 + 0.115597e9 + 4.056275e9 + 0.114527e9) / 2.0
 
 
 def load_peaks():
@@ -384,7 +384,7 @@ def main():
         roofline = {"bound": "hbm", "kernel": "k_gram<7,USER|ITEM,SOLVE>", "achieved": achieved,
                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": (NCU_DRAM_BYTES_PER_LAUNCH_C3 / world if not args.small else None),
-                    "traffic_source": "profiles/ncu_k_gram_C3_r01_v3.txt (1 GPU capture)",
+                    "traffic_source": "profiles/ncu_k_gram_C3_r01_v4.txt (1 GPU capture)",
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes / 2.0 / world,
                     "avg_launch_ms": per_launch_ms,

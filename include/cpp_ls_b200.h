@@ -226,6 +226,50 @@ MRB_API int mrb_cosim_query(mrb_cosim* h, int q_lo, int q_hi, const double* buff
                             float* kernel_ms);
 MRB_API void mrb_cosim_destroy(mrb_cosim* h);
 
+/* ------------------------------------------------------------------------------------------
+ * 8. Extensions: ALS data preparation -- the step right before the
+ *    hot path.  The reference does it in multi-process Python, there is no FFI to bind; the two
+ *    entry points below take the flattened form of its in-memory lists
+ *    `user_ratings_train = [(user id, [(movie id, rating)])]`: one entry per rating in list
+ *    order, `user_slot_ids[i]` = index of the rating's user entry in the list, `movie_ids[i]` =
+ *    the (non-negative) movie id, used directly as a slot number < num_movie_slots.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Replaces the median step of refresh_training_sets_mp (python/full_data/movie_lens_data.py:
+ * 453-464; workers movie_lens_data_proc.py:393-431 _extract_movie_ratings, :455-471
+ * _compute_medians): medians_out[m] = numpy.median of movie m's ratings (the middle element, or
+ * (a + b) / 2 of the two middle elements), NaN when the movie has none; counts_out[m] = how many.
+ * Bit-exact.  NaN ratings are not supported (the reference's data cannot hold them). */
+MRB_API int mrb_movie_medians(const int* movie_ids, const double* ratings, int num_ratings,
+                              int num_movie_slots, double* medians_out, int* counts_out,
+                              float* kernel_ms);
+
+typedef struct mrb_shrink_info {
+    int num_ratings_out;   /* surviving ratings */
+    int num_users_out;     /* surviving users  = len(als_user_ids)  */
+    int num_movies_out;    /* surviving movies = len(als_movie_ids) */
+    int rounds;            /* passes of the reference's `while has_changed` loop */
+    float kernel_ms;       /* CUDA-event time of the device work (copies excluded) */
+} mrb_shrink_info;
+
+/* Replaces als_data_set_shrink_mp for one factor (movie_lens_data.py:569-645; workers
+ * movie_lens_data_proc.py:494-535 _drop_users, :538-556 _count_movies, :559-586 _drop_movies,
+ * :589-608 _collect_ids, :611-654 _convert_training_data_to_numpy): users with fewer than
+ * min_user_ratings (= factor + 1) and movies with fewer than min_movie_ratings (= factor)
+ * surviving ratings are dropped alternately until nothing changes; the surviving ratings are
+ * written in their original order (capacity num_ratings) as zero-based user id, zero-based movie
+ * id and rating - medians[movie]; keep_pos_out[j] = original position of output j.
+ * user_new_id[num_user_slots] / movie_new_id[num_movie_slots] = new id or -1.
+ * Ids are renumbered in ASCENDING slot order.  (The reference numbers them in the iteration order
+ * of a Python set merged from its worker processes, movie_lens_data.py:590-609 -- a relabelling
+ * that depends on the worker count; the Python mirror can re-apply the single-process order.) */
+MRB_API int mrb_als_shrink(const int* user_slot_ids, const int* movie_ids, const double* ratings,
+                           int num_ratings, int num_user_slots, int num_movie_slots,
+                           const double* medians, int min_user_ratings, int min_movie_ratings,
+                           int* user_ids_out, int* movie_ids_out, double* ratings_out,
+                           int* keep_pos_out, int* user_new_id, int* movie_new_id,
+                           mrb_shrink_info* info);
+
 #ifdef __cplusplus
 }
 #endif

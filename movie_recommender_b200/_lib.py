@@ -36,6 +36,13 @@ class SimInfo(ctypes.Structure):
                 ("fallback_rows", ctypes.c_int)]
 
 
+class ShrinkInfo(ctypes.Structure):
+    """mrb_shrink_info (include/cpp_ls_b200.h)."""
+    _fields_ = [("num_ratings_out", ctypes.c_int), ("num_users_out", ctypes.c_int),
+                ("num_movies_out", ctypes.c_int), ("rounds", ctypes.c_int),
+                ("kernel_ms", ctypes.c_float)]
+
+
 class CppLsError(RuntimeError):
     def __init__(self, code, message):
         super().__init__("cpp_ls_lib error %d: %s" % (code, message))
@@ -120,6 +127,11 @@ def _declare(dll):
                                     ctypes.POINTER(ctypes.c_float)]
     dll.mrb_cosim_destroy.restype = None
     dll.mrb_cosim_destroy.argtypes = [c_void_p]
+    dll.mrb_movie_medians.restype = c_int
+    dll.mrb_movie_medians.argtypes = [_I, _D, c_int, c_int, _D, _I, ctypes.POINTER(ctypes.c_float)]
+    dll.mrb_als_shrink.restype = c_int
+    dll.mrb_als_shrink.argtypes = [_I, _I, _D, c_int, c_int, c_int, _D, c_int, c_int, _I, _I, _D,
+                                   _I, _I, _I, ctypes.POINTER(ShrinkInfo)]
     dll.mrb_trim_memory.restype = None
     dll.mrb_trim_memory.argtypes = []
     dll.mrb_kernel_launches.restype = ctypes.c_longlong

@@ -16,6 +16,7 @@
 #include "ls_native.cuh"
 #include "similarity.cuh"
 #include "cosim.cuh"
+#include "prep.cuh"
 
 namespace mrb {
 static thread_local std::string g_last_error;
@@ -504,6 +505,106 @@ int mrb_cosine_topk(const double* factors, int num_items, int num_factors, int t
             info->candidates_ms = r.candidates_ms;
             info->total_ms = r.total_ms;
             info->fallback_rows = r.fallback_rows;
+        }
+        return 0;
+    });
+}
+
+// ------------------------------------------------------------------ section 8: data preparation
+namespace {
+struct PrepStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    PrepStream() {
+        MRB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        MRB_CUDA(cudaEventCreate(&e0));
+        MRB_CUDA(cudaEventCreate(&e1));
+    }
+    ~PrepStream() {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (s) cudaStreamDestroy(s);
+    }
+    float elapsed() {
+        float ms = 0.f;
+        MRB_CUDA(cudaEventSynchronize(e1));
+        MRB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        return ms;
+    }
+};
+}  // namespace
+
+int mrb_movie_medians(const int* movie_ids, const double* ratings, int num_ratings,
+                      int num_movie_slots, double* medians_out, int* counts_out, float* kernel_ms) {
+    return guarded([&] {
+        MRB_REQUIRE(num_ratings >= 0 && num_movie_slots >= 0, "mrb_movie_medians: negative size");
+        MRB_REQUIRE(num_ratings == 0 || (movie_ids != nullptr && ratings != nullptr),
+                    "mrb_movie_medians: null input");
+        MRB_REQUIRE(num_movie_slots == 0 || (medians_out != nullptr && counts_out != nullptr),
+                    "mrb_movie_medians: null output");
+        PrepStream ps;
+        const size_t n = static_cast<size_t>(num_ratings), ms = static_cast<size_t>(num_movie_slots);
+        DevBuf<int> d_movie(n), d_count(ms);
+        DevBuf<double> d_rating(n), d_median(ms);
+        d_movie.upload(movie_ids, n, ps.s);
+        d_rating.upload(ratings, n, ps.s);
+        check_id_range(d_movie.p, num_ratings, num_movie_slots, "mrb_movie_medians: movie_ids", ps.s);
+        MRB_CUDA(cudaEventRecord(ps.e0, ps.s));
+        movie_medians(d_movie.p, d_rating.p, num_ratings, num_movie_slots, d_median.p, d_count.p, ps.s);
+        MRB_CUDA(cudaEventRecord(ps.e1, ps.s));
+        d_median.download(medians_out, ms, ps.s);
+        d_count.download(counts_out, ms, ps.s);
+        MRB_CUDA(cudaStreamSynchronize(ps.s));
+        if (kernel_ms) *kernel_ms = ps.elapsed();
+        return 0;
+    });
+}
+
+int mrb_als_shrink(const int* user_slot_ids, const int* movie_ids, const double* ratings,
+                   int num_ratings, int num_user_slots, int num_movie_slots, const double* medians,
+                   int min_user_ratings, int min_movie_ratings, int* user_ids_out,
+                   int* movie_ids_out, double* ratings_out, int* keep_pos_out, int* user_new_id,
+                   int* movie_new_id, mrb_shrink_info* info) {
+    return guarded([&] {
+        MRB_REQUIRE(num_ratings >= 0 && num_user_slots >= 0 && num_movie_slots >= 0,
+                    "mrb_als_shrink: negative size");
+        MRB_REQUIRE(num_ratings == 0 || (user_slot_ids && movie_ids && ratings && user_ids_out &&
+                                         movie_ids_out && ratings_out && keep_pos_out),
+                    "mrb_als_shrink: null rating array");
+        MRB_REQUIRE((num_user_slots == 0 || user_new_id) && (num_movie_slots == 0 || (movie_new_id && medians)),
+                    "mrb_als_shrink: null id table / medians");
+        PrepStream ps;
+        const size_t n = static_cast<size_t>(num_ratings), us = static_cast<size_t>(num_user_slots),
+                     ms = static_cast<size_t>(num_movie_slots);
+        DevBuf<int> d_user(n), d_movie(n), d_out_user(n), d_out_movie(n), d_keep(n), d_user_new(us),
+            d_movie_new(ms);
+        DevBuf<double> d_rating(n), d_out_rating(n), d_median(ms);
+        d_user.upload(user_slot_ids, n, ps.s);
+        d_movie.upload(movie_ids, n, ps.s);
+        d_rating.upload(ratings, n, ps.s);
+        d_median.upload(medians, ms, ps.s);
+        check_id_range(d_user.p, num_ratings, num_user_slots, "mrb_als_shrink: user_slot_ids", ps.s);
+        check_id_range(d_movie.p, num_ratings, num_movie_slots, "mrb_als_shrink: movie_ids", ps.s);
+        MRB_CUDA(cudaEventRecord(ps.e0, ps.s));
+        const ShrinkCounts c = als_shrink(d_user.p, d_movie.p, d_rating.p, num_ratings, num_user_slots,
+                                          num_movie_slots, d_median.p, min_user_ratings,
+                                          min_movie_ratings, d_out_user.p, d_out_movie.p,
+                                          d_out_rating.p, d_keep.p, d_user_new.p, d_movie_new.p, ps.s);
+        MRB_CUDA(cudaEventRecord(ps.e1, ps.s));
+        const size_t m = static_cast<size_t>(c.ratings_out);
+        d_out_user.download(user_ids_out, m, ps.s);
+        d_out_movie.download(movie_ids_out, m, ps.s);
+        d_out_rating.download(ratings_out, m, ps.s);
+        d_keep.download(keep_pos_out, m, ps.s);
+        d_user_new.download(user_new_id, us, ps.s);
+        d_movie_new.download(movie_new_id, ms, ps.s);
+        MRB_CUDA(cudaStreamSynchronize(ps.s));
+        if (info) {
+            info->num_ratings_out = c.ratings_out;
+            info->num_users_out = c.users_out;
+            info->num_movies_out = c.movies_out;
+            info->rounds = c.rounds;
+            info->kernel_ms = ps.elapsed();
         }
         return 0;
     });

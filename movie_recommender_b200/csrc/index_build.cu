@@ -230,6 +230,50 @@ void stable_group_by(const int* d_key, int n, int num_groups, int* d_ptr, int* d
     MRB_CUDA(cudaStreamSynchronize(s));  // temporaries are freed on return
 }
 
+void stable_sort_pairs(const int* d_key, const int* d_val_in, int n, unsigned digit_mask,
+                       int* d_key_out, int* d_val_out, cudaStream_t s) {
+    MRB_REQUIRE(n >= 0, "stable_sort_pairs: negative size");
+    if (n == 0) return;
+    MRB_REQUIRE(d_key != d_key_out && d_val_in != d_val_out, "stable_sort_pairs: aliased buffers");
+    digit_mask &= 0xFu;
+    const int passes = __builtin_popcount(digit_mask);
+    if (passes == 0) {
+        MRB_CUDA(cudaMemcpyAsync(d_key_out, d_key, sizeof(int) * static_cast<size_t>(n),
+                                 cudaMemcpyDeviceToDevice, s));
+        if (d_val_in) {
+            MRB_CUDA(cudaMemcpyAsync(d_val_out, d_val_in, sizeof(int) * static_cast<size_t>(n),
+                                     cudaMemcpyDeviceToDevice, s));
+        } else {
+            k_iota<<<ceil_div(n, 256), 256, 0, s>>>(d_val_out, n); MRB_LAUNCHED(1);
+            MRB_CUDA(cudaGetLastError());
+        }
+        return;
+    }
+    const int num_blocks = ceil_div(n, RS_TILE);
+    DevBuf<int> hist(static_cast<size_t>(256) * num_blocks);
+    DevBuf<int> key_t(passes > 1 ? n : 0), val_t(passes > 1 ? n : 0);
+    const int* kin = d_key;
+    const int* vin = d_val_in;
+    int done = 0;
+    for (int d = 0; d < 4; d++) {
+        if (!((digit_mask >> d) & 1u)) continue;
+        // alternate between the temporaries and the outputs so that the LAST pass lands in the outputs
+        const bool to_out = ((passes - 1 - done) & 1) == 0;
+        int* kout = to_out ? d_key_out : key_t.p;
+        int* vout = to_out ? d_val_out : val_t.p;
+        k_radix_hist<<<num_blocks, RS_THREADS, 0, s>>>(kin, n, 8 * d, hist.p, num_blocks); MRB_LAUNCHED(1);
+        MRB_CUDA(cudaGetLastError());
+        exclusive_scan_i32(hist.p, hist.p, static_cast<long long>(256) * num_blocks, s);
+        k_radix_scatter<<<num_blocks, RS_THREADS, 0, s>>>(kin, vin, n, 8 * d, hist.p, num_blocks,
+                                                           kout, vout); MRB_LAUNCHED(1);
+        MRB_CUDA(cudaGetLastError());
+        kin = kout;
+        vin = vout;
+        done++;
+    }
+    MRB_CUDA(cudaStreamSynchronize(s));  // temporaries are freed on return
+}
+
 // ------------------------------------------------------------------------------------------
 // Explicit transpose.
 // ------------------------------------------------------------------------------------------

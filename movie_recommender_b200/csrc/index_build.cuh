@@ -15,6 +15,13 @@ void exclusive_scan_i32(const int* d_in, int* d_out, long long n, cudaStream_t s
 void stable_group_by(const int* d_key, int n, int num_groups, int* d_ptr, int* d_idx,
                      cudaStream_t s);
 
+// Stable LSD radix sort of (key, value) pairs on selected 8-bit digits of the 32-bit key: bit d
+// of digit_mask selects bits 8d..8d+7 (unselected digits are ignored, e.g. because every key
+// carries the same value there).  d_val_in == nullptr means value i = i.  Outputs must not
+// alias the inputs.  With digit_mask == 0 the pairs are copied through unchanged.
+void stable_sort_pairs(const int* d_key, const int* d_val_in, int n, unsigned digit_mask,
+                       int* d_key_out, int* d_val_out, cudaStream_t s);
+
 // Stable CSR -> CSC (explicit transpose), matrix.cpp:617-692: for every column the entries in
 // ascending (row, position-in-row) order.  Outputs: t_ptr[cols+1], t_row[nnz], t_val[nnz].
 void csr_transpose(int rows, int cols, int nnz, const int* d_rowptr, const int* d_colidx,
