@@ -43,6 +43,10 @@ constexpr int GRAM_WARPS = 4;      // warps per CTA
 #define GRAM_RING_ITEM 5           // item half-sweep (the user factors spill out of L2)
 #endif
 
+#ifndef GRAM_DEFAULT_ORDER
+#define GRAM_DEFAULT_ORDER 0
+#endif
+
 struct WorkItem {
     int owner;   // row of the factor matrix being solved
     int beg;     // first grouped rating position
@@ -93,9 +97,20 @@ struct GramArgs {
     double* x_peers[8];       // other replicas of the owner factor matrix (NVLink peer memory)
     int n_peers;              // number of entries of x_peers (0 on a single GPU)
     int debug_skip_solve;     // MRB_DEBUG_SKIP_SOLVE=1: time the accumulation alone (results invalid)
+    int order_mode;           // how scheduler tickets map to the degree-sorted work list (work_index)
 };
 
 enum { EPI_SOLVE = 0, EPI_STORE = 1 };
+
+// Ticket -> position in the work list (sorted longest first).
+//   0: in list order (longest processing time first);
+//   1: alternately from the heavy and from the light end, so that the two warps sharing a
+//      scheduler tend to pair a tensor-bound accumulation with a latency-bound solve; the last
+//      tickets are median-sized owners, so the tail stays short.
+__device__ __forceinline__ int work_index(int w, int n_work, int mode) {
+    if (mode == 1) return (w & 1) ? n_work - 1 - (w >> 1) : (w >> 1);
+    return w;
+}
 
 __device__ double g_zero_row[64];   // zero-initialised: the factor row of a padding rating
 
@@ -384,7 +399,7 @@ k_gram(const GramArgs A) {
     if (lane == 0) ticket = atomicAdd(A.work_counter, 1);
     int w = __shfl_sync(0xffffffffu, ticket, 0);
     WorkItem wi_next{};
-    if (w < A.n_work) wi_next = A.work[w];
+    if (w < A.n_work) wi_next = A.work[work_index(w, A.n_work, A.order_mode)];
     for (;;) {
         if (w >= A.n_work) break;
         const WorkItem wi = wi_next;
@@ -392,7 +407,7 @@ k_gram(const GramArgs A) {
         // every path to the next iteration goes through advance()
         auto advance = [&]() {
             w = __shfl_sync(0xffffffffu, ticket, 0);
-            if (w < A.n_work) wi_next = A.work[w];
+            if (w < A.n_work) wi_next = A.work[work_index(w, A.n_work, A.order_mode)];
         };
 
 #ifndef GRAM_NO_X0_PREFETCH
@@ -1243,6 +1258,8 @@ void AlsProblem::launch_half(bool user_side, cudaStream_t stream, int epilogue) 
     a.seg_done = g.counters.p + 1;
     a.debug_skip_solve = std::getenv("MRB_DEBUG_SKIP_SOLVE") != nullptr
                              ? std::atoi(std::getenv("MRB_DEBUG_SKIP_SOLVE")) : 0;
+    a.order_mode = std::getenv("MRB_WORK_ORDER") != nullptr ? std::atoi(std::getenv("MRB_WORK_ORDER"))
+                                                            : GRAM_DEFAULT_ORDER;
     a.n_peers = 0;
     const std::vector<double*>& peers = user_side ? uf_peers_ : itf_peers_;
     for (size_t j = 0; j < peers.size(); j++)

@@ -47,11 +47,14 @@ k_rating_keys(const double* __restrict__ rating, int n, int* __restrict__ key_lo
     lo_and = __reduce_and_sync(0xffffffffu, lo_and);
     hi_or = __reduce_or_sync(0xffffffffu, hi_or);
     hi_and = __reduce_and_sync(0xffffffffu, hi_and);
+    // the four words saturate after a few warps: look before touching them (867 k warps hitting
+    // the same four addresses with atomics cost 2.4 ms at 27.75 M ratings, the look-up nothing)
     if ((threadIdx.x & 31) == 0) {
-        atomicOr(&orand[0], lo_or);
-        atomicAnd(&orand[1], lo_and);
-        atomicOr(&orand[2], hi_or);
-        atomicAnd(&orand[3], hi_and);
+        const volatile unsigned* seen = orand;
+        if ((seen[0] | lo_or) != seen[0]) atomicOr(&orand[0], lo_or);
+        if ((seen[1] & lo_and) != seen[1]) atomicAnd(&orand[1], lo_and);
+        if ((seen[2] | hi_or) != seen[2]) atomicOr(&orand[2], hi_or);
+        if ((seen[3] & hi_and) != seen[3]) atomicAnd(&orand[3], hi_and);
     }
 }
 
