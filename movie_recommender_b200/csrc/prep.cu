@@ -3,6 +3,8 @@
 // results are deterministic and bit-exact against the reference's Python.
 #include "prep.cuh"
 
+#include <algorithm>
+
 #include "index_build.cuh"
 
 namespace mrb {
@@ -33,28 +35,31 @@ __device__ __forceinline__ unsigned long long orderable(double v) {
 __global__ void __launch_bounds__(PT)
 k_rating_keys(const double* __restrict__ rating, int n, int* __restrict__ key_lo,
               int* __restrict__ key_hi, unsigned* __restrict__ orand) {
-    const int i = blockIdx.x * PT + threadIdx.x;
+    // persistent grid-stride CTAs (a multiple of the SM count): the OR/AND words are combined in
+    // registers and reach the four global words once per warp of the whole grid.  (One atomic
+    // -- or even one look -- per 32 ratings made 867 k warps queue on a single L2 line: 2.4 ms
+    // for a kernel that streams 444 MB.)
     unsigned lo_or = 0u, lo_and = 0xFFFFFFFFu, hi_or = 0u, hi_and = 0xFFFFFFFFu;
-    if (i < n) {
+    const long long stride = static_cast<long long>(gridDim.x) * PT;
+    for (long long i = static_cast<long long>(blockIdx.x) * PT + threadIdx.x; i < n; i += stride) {
         const unsigned long long k = orderable(rating[i]);
         const unsigned lo = static_cast<unsigned>(k), hi = static_cast<unsigned>(k >> 32);
         key_lo[i] = static_cast<int>(lo);
         key_hi[i] = static_cast<int>(hi);
-        lo_or = lo_and = lo;
-        hi_or = hi_and = hi;
+        lo_or |= lo;
+        lo_and &= lo;
+        hi_or |= hi;
+        hi_and &= hi;
     }
     lo_or = __reduce_or_sync(0xffffffffu, lo_or);
     lo_and = __reduce_and_sync(0xffffffffu, lo_and);
     hi_or = __reduce_or_sync(0xffffffffu, hi_or);
     hi_and = __reduce_and_sync(0xffffffffu, hi_and);
-    // the four words saturate after a few warps: look before touching them (867 k warps hitting
-    // the same four addresses with atomics cost 2.4 ms at 27.75 M ratings, the look-up nothing)
     if ((threadIdx.x & 31) == 0) {
-        const volatile unsigned* seen = orand;
-        if ((seen[0] | lo_or) != seen[0]) atomicOr(&orand[0], lo_or);
-        if ((seen[1] & lo_and) != seen[1]) atomicAnd(&orand[1], lo_and);
-        if ((seen[2] | hi_or) != seen[2]) atomicOr(&orand[2], hi_or);
-        if ((seen[3] & hi_and) != seen[3]) atomicAnd(&orand[3], hi_and);
+        atomicOr(&orand[0], lo_or);
+        atomicAnd(&orand[1], lo_and);
+        atomicOr(&orand[2], hi_or);
+        atomicAnd(&orand[3], hi_and);
     }
 }
 
@@ -219,7 +224,7 @@ void movie_medians(const int* d_movie, const double* d_rating, int n, int movie_
         DevBuf<unsigned> orand(4);
         const unsigned init[4] = {0u, 0xFFFFFFFFu, 0u, 0xFFFFFFFFu};
         MRB_CUDA(cudaMemcpyAsync(orand.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
-        k_rating_keys<<<blocks, PT, 0, s>>>(d_rating, n, key_lo.p, key_hi.p, orand.p); MRB_LAUNCHED(1);
+        k_rating_keys<<<std::min(blocks, 148 * 8), PT, 0, s>>>(d_rating, n, key_lo.p, key_hi.p, orand.p); MRB_LAUNCHED(1);
         MRB_CUDA(cudaGetLastError());
         unsigned h[4];
         MRB_CUDA(cudaMemcpyAsync(h, orand.p, sizeof(h), cudaMemcpyDeviceToHost, s));
