@@ -49,29 +49,35 @@ k_csr_mul_warp(const int* __restrict__ rowptr, const int* __restrict__ colidx,
     if (lane == 0) y[r] = s;
 }
 
-// One warp per (column, row-block) segment: lanes stride over the segment, fixed-order xor
-// reduction.  Splitting the rows into 64 equal blocks bounds the longest segment, so that a movie
-// column with 55 000 entries is spread over 64 warps instead of serialising one.
+// G lanes per (column, row-block) segment (G = 8, 16 or 32, chosen from the mean segment length):
+// the lanes stride over the segment, fixed-order xor reduction inside the group.  Splitting the
+// rows into 64 equal blocks bounds the longest segment, so that a movie column with 55 000
+// entries is spread over 64 groups instead of serialising one.  With a full warp per segment the
+// kernel ran at the latency of its dependent chain (bounds -> row/value -> gather of t) with 15
+// useful elements per warp at config 2 (ncu: 21 % of the HBM peak at 80 % occupancy, issue slots
+// 30 % busy); 8-lane groups put four segments in flight per warp.
+template <int G>
 __global__ void __launch_bounds__(256)
 k_csc_seg_native(const int* __restrict__ seg_start, int nseg, const int* __restrict__ t_row,
                  const double* __restrict__ t_val, const double* __restrict__ t,
                  double* __restrict__ partial, const CgState* __restrict__ guard) {
     if (guard && guard->done) return;
-    const int sg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (sg >= nseg) return;
-    const int lane = threadIdx.x & 31;
-    const int beg = seg_start[sg], end = seg_start[sg + 1];
+    const long long gid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+    const int sub = threadIdx.x & (G - 1);
+    // every lane of the warp stays in the shuffles below; groups past the end carry empty ranges
+    const bool live = gid < nseg;
+    const int beg = live ? seg_start[gid] : 0, end = live ? seg_start[gid + 1] : 0;
     double s0 = 0, s1 = 0;
-    int e = beg + lane;
-    for (; e + 32 < end; e += 64) {
+    int e = beg + sub;
+    for (; e + G < end; e += 2 * G) {
         s0 += t_val[e] * t[t_row[e]];
-        s1 += t_val[e + 32] * t[t_row[e + 32]];
+        s1 += t_val[e + G] * t[t_row[e + G]];
     }
     if (e < end) s0 += t_val[e] * t[t_row[e]];
     double s = s0 + s1;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) partial[sg] = s;
+    for (int off = G / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (sub == 0 && live) partial[gid] = s;
 }
 
 // out[c] = sum of the column's segment sums in block order; dots[c] = v[c] * out[c]
@@ -169,9 +175,18 @@ LsNativeResult solve_ls_native(int rows, int cols, const int* rowptr, const int*
     build_segments(seg, t_ptr.p, t_row.p, cols, nnz, d_bounds.p, kRowBlocks, 1, s);
     auto tmul = [&](const double* t, const double* v, double* out, double* dd, const CgState* guard) {
         if (cols == 0) return;
-        if (seg.nseg > 0)
-            k_csc_seg_native<<<ceil_div(static_cast<long long>(seg.nseg) * 32, 256), 256, 0, s>>>(
-                seg.seg_start.p, seg.nseg, t_row.p, t_val.p, t, seg.partial.p, guard);
+        if (seg.nseg > 0) {
+            const long long mean_len = nnz / seg.nseg;
+            if (mean_len < 24)
+                k_csc_seg_native<8><<<ceil_div(static_cast<long long>(seg.nseg) * 8, 256), 256, 0, s>>>(
+                    seg.seg_start.p, seg.nseg, t_row.p, t_val.p, t, seg.partial.p, guard);
+            else if (mean_len < 48)
+                k_csc_seg_native<16><<<ceil_div(static_cast<long long>(seg.nseg) * 16, 256), 256, 0, s>>>(
+                    seg.seg_start.p, seg.nseg, t_row.p, t_val.p, t, seg.partial.p, guard);
+            else
+                k_csc_seg_native<32><<<ceil_div(static_cast<long long>(seg.nseg) * 32, 256), 256, 0, s>>>(
+                    seg.seg_start.p, seg.nseg, t_row.p, t_val.p, t, seg.partial.p, guard);
+        }
         k_csc_fold_native<<<ceil_div(cols, 256), 256, 0, s>>>(seg.grp_seg_ptr.p, seg.partial.p, v, out,
                                                             dd, cols, guard);
         MRB_LAUNCHED(2);

@@ -113,23 +113,36 @@ unsigned digits_that_vary(unsigned or_bits, unsigned and_bits) {
 
 // ---------------------------------------------------------------------------------- shrink
 // cnt[key] += 1 for every rating whose user AND movie are still in (warp-aggregated: ratings
-// are grouped by user, so a warp usually carries one or two users).
+// are grouped by user, so a warp usually carries one or two users).  Each thread carries CA_ILP
+// ratings (PT apart, so every load stays coalesced) and issues all its id loads, then all its
+// flag gathers, before the first vote: with one rating per thread the kernel ran at the latency
+// of the dependent chain id -> flag -> atomic (1.98 TB/s of the id streams at 80 % occupancy).
+constexpr int CA_ILP = 4;
 __global__ void __launch_bounds__(PT)
 k_count_alive(const int* __restrict__ user, const int* __restrict__ movie, int n,
               const int* __restrict__ user_ok, const int* __restrict__ movie_ok, int by_user,
               int* __restrict__ cnt) {
-    const int i = blockIdx.x * PT + threadIdx.x;
-    bool alive = false;
-    int key = -1;
-    if (i < n) {
-        const int u = user[i], m = movie[i];
-        alive = user_ok[u] != 0 && movie_ok[m] != 0;
-        key = by_user ? u : m;
+    const long long base = static_cast<long long>(blockIdx.x) * (PT * CA_ILP) + threadIdx.x;
+    int u[CA_ILP], m[CA_ILP];
+    bool alive[CA_ILP];
+#pragma unroll
+    for (int j = 0; j < CA_ILP; j++) {
+        const long long i = base + j * PT;
+        u[j] = i < n ? user[i] : -1;
+        m[j] = i < n ? movie[i] : -1;
     }
-    const unsigned act = __ballot_sync(0xffffffffu, alive);
-    if (!alive) return;
-    const unsigned peers = __match_any_sync(act, key);
-    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cnt[key], __popc(peers));
+#pragma unroll
+    for (int j = 0; j < CA_ILP; j++)
+        alive[j] = u[j] >= 0 && user_ok[u[j]] != 0 && movie_ok[m[j]] != 0;
+#pragma unroll
+    for (int j = 0; j < CA_ILP; j++) {
+        const int key = by_user ? u[j] : m[j];
+        const unsigned act = __ballot_sync(0xffffffffu, alive[j]);
+        if (alive[j]) {
+            const unsigned peers = __match_any_sync(act, key);
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cnt[key], __popc(peers));
+        }
+    }
 }
 
 // ok[s] &= cnt[s] >= min_count.  *changed is raised the way the reference raises has_changed:
@@ -277,7 +290,7 @@ ShrinkCounts als_shrink(const int* d_user, const int* d_movie, const double* d_r
         MRB_CUDA(cudaMemsetAsync(user_cnt.p, 0, sizeof(int) * (static_cast<size_t>(user_slots) + 1), s));
         MRB_CUDA(cudaMemsetAsync(movie_cnt.p, 0, sizeof(int) * (static_cast<size_t>(movie_slots) + 1), s));
         if (n > 0) {
-            k_count_alive<<<ceil_div(n, PT), PT, 0, s>>>(d_user, d_movie, n, user_ok.p, movie_ok.p, 1,
+            k_count_alive<<<ceil_div(n, PT * CA_ILP), PT, 0, s>>>(d_user, d_movie, n, user_ok.p, movie_ok.p, 1,
                                                         user_cnt.p); MRB_LAUNCHED(1);
         }
         if (user_slots > 0) {
@@ -285,7 +298,7 @@ ShrinkCounts als_shrink(const int* d_user, const int* d_movie, const double* d_r
                                                                 min_user, 0, changed.p); MRB_LAUNCHED(1);
         }
         if (n > 0) {
-            k_count_alive<<<ceil_div(n, PT), PT, 0, s>>>(d_user, d_movie, n, user_ok.p, movie_ok.p, 0,
+            k_count_alive<<<ceil_div(n, PT * CA_ILP), PT, 0, s>>>(d_user, d_movie, n, user_ok.p, movie_ok.p, 0,
                                                         movie_cnt.p); MRB_LAUNCHED(1);
         }
         if (movie_slots > 0) {

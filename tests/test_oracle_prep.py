@@ -89,3 +89,32 @@ def test_single_process_set_order_is_a_relabelling():
     users, movies = po.reference_set_order(train)
     assert sorted(users.values()) == list(range(len(users)))
     assert len(movies) == int(g["k3_num_movies"])
+
+
+def test_the_two_forms_agree_on_random_inputs():
+    """Property test (hypothesis): list form == COO form on arbitrary small rating sets,
+    including users without ratings, repeated movies inside a user and rules that empty the set."""
+    from hypothesis import given, settings, strategies as st
+
+    entry = st.tuples(st.integers(0, 11), st.sampled_from([0.5, 1.0, 2.5, 3.0, 4.5, 5.0]))
+    users = st.lists(st.lists(entry, max_size=9), min_size=1, max_size=14)
+
+    @settings(max_examples=150, deadline=None)
+    @given(users, st.integers(1, 4))
+    def check(user_lists, k):
+        train = [(10 + 3 * u, e) for u, e in enumerate(user_lists)]
+        up, raw_u, mr, r = po.flatten(train)
+        slots_m = 12
+        med, cnt = po.medians_coo(mr, r, slots_m) if len(r) else (np.full(slots_m, np.nan), np.zeros(slots_m, np.int32))
+        med_l = po.medians_lists(train)
+        assert sorted(med_l) == np.nonzero(cnt)[0].tolist()
+        assert bits_equal([med_l[m] for m in sorted(med_l)], med[cnt > 0])
+        shrunk, _, rounds = po.shrink_lists(train, k)
+        s = po.shrink_coo(up, mr, r, len(raw_u), slots_m, med, k + 1, k)
+        assert rounds == s["rounds"]
+        users_l, movies_l = po.sorted_order(shrunk)
+        u, m, rr = po.convert_lists(shrunk, med_l, users_l, movies_l)
+        assert np.array_equal(u, s["user_ids"]) and np.array_equal(m, s["movie_ids"])
+        assert bits_equal(rr, s["ratings"])
+
+    check()

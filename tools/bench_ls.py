@@ -13,13 +13,15 @@ ap.add_argument("--items", type=int, default=53889)
 ap.add_argument("--ratings", type=int, default=27753444)
 ap.add_argument("--cpu-rows", type=int, default=4000000)
 ap.add_argument("--faithful", action="store_true", help="also time the bit-faithful algorithm 1")
+ap.add_argument("--no-warmup", action="store_true", help="skip the small warm-up solve (ncu captures)")
 a = ap.parse_args()
 
 u, i = synth.rating_pairs(a.users, a.items, a.ratings, 51, 50)
 raw = synth.planted_ratings(u, i, a.users, a.items, subtract_median=False)
 rowptr, col, vals, cols, b, x0 = synth.bias_model_system(u, i, raw, a.users, a.items)
 rows, nnz = len(b), len(vals)
-cpp_ls.cg_least_squares(rowptr[:1001], col[:2000], vals[:2000], cols, b[:1000], algorithm=3, x0=x0)  # warm-up
+if not a.no_warmup:
+    cpp_ls.cg_least_squares(rowptr[:1001], col[:2000], vals[:2000], cols, b[:1000], algorithm=3, x0=x0)  # warm-up
 t0 = time.time()
 x, it, rr = cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, algorithm=3, x0=x0)
 wall = time.time() - t0
