@@ -10,6 +10,8 @@
 //   2*nnz_A*(8+4) + (rows+cols+2)*4 + rows*8 + nnz_A*8 + 7*cols*8.
 #include "ls_native.cuh"
 
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "faithful_cg.cuh"
@@ -78,6 +80,78 @@ k_csc_seg_native(const int* __restrict__ seg_start, int nseg, const int* __restr
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (sub == 0 && live) partial[gid] = s;
+}
+
+// ---- flat A^T t: the transposed entries are cut into WINDOWS of 32 consecutive entries; a piece
+// is (column intersected with a window).  heads[w] has bit b set where entry 32 w + b starts a
+// piece (bit 0 always), win_first[w] = number of pieces before window w.  One lane per entry:
+// perfectly coalesced index / value streams, no per-segment dependent chain, the same number of
+// entries per lane whatever the column lengths; the pieces of a column are then added in order
+// by k_csc_fold_native.  Deterministic (fixed shuffle tree inside a window, ordered fold).
+__global__ void k_flat_init_heads(unsigned* __restrict__ heads, int nwords) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w <= nwords) heads[w] = w < nwords ? 1u : 0u;
+}
+
+__global__ void k_flat_mark_heads(const int* __restrict__ t_ptr, int cols, unsigned* __restrict__ heads) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const int e = t_ptr[c];
+    if (e < t_ptr[c + 1]) atomicOr(&heads[e >> 5], 1u << (e & 31));
+}
+
+__global__ void k_flat_popc(const unsigned* __restrict__ heads, int nwords, int* __restrict__ cnt) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w <= nwords) cnt[w] = __popc(heads[w]);
+}
+
+// col_piece_ptr[c] = number of pieces that start before entry t_ptr[c]  (c = 0 .. cols)
+__global__ void k_flat_col_ptr(const int* __restrict__ t_ptr, int cols,
+                               const unsigned* __restrict__ heads, const int* __restrict__ win_first,
+                               int* __restrict__ col_piece_ptr) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > cols) return;
+    const int e = t_ptr[c], w = e >> 5, b = e & 31;
+    col_piece_ptr[c] = win_first[w] + __popc(heads[w] & ((1u << b) - 1u));
+}
+
+template <int WPW>   // windows per warp: all index/value loads, then all gathers, then the scans
+__global__ void __launch_bounds__(256)
+k_csc_flat(const unsigned* __restrict__ heads, const int* __restrict__ win_first,
+           const int* __restrict__ t_row, const double* __restrict__ t_val,
+           const double* __restrict__ t, double* __restrict__ partial, int nnz, int nwords,
+           const CgState* __restrict__ guard) {
+    if (guard && guard->done) return;
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * WPW;
+    int row[WPW], first[WPW];
+    double val[WPW];
+    unsigned hd[WPW];
+#pragma unroll
+    for (int j = 0; j < WPW; j++) {
+        const long long w = w0 + j, e = w * 32 + lane;
+        const bool win = w < nwords, ok = win && e < nnz;
+        row[j] = ok ? t_row[e] : -1;
+        val[j] = ok ? t_val[e] : 0.0;
+        hd[j] = win ? heads[w] : 0u;
+        first[j] = win ? win_first[w] : 0;
+    }
+    double prod[WPW];
+#pragma unroll
+    for (int j = 0; j < WPW; j++) prod[j] = row[j] >= 0 ? val[j] * t[row[j]] : 0.0;
+#pragma unroll
+    for (int j = 0; j < WPW; j++) {
+        const unsigned below = hd[j] & (0xffffffffu >> (31 - lane));   // heads at or before this lane
+        const int head = 31 - __clz(below);                             // -1 for a window past the end
+        double v = prod[j];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane - d >= head) v += o;
+        }
+        const bool last = lane == 31 || ((hd[j] >> (lane + 1)) & 1u);
+        if (hd[j] != 0u && last) partial[first[j] + __popc(below) - 1] = v;
+    }
 }
 
 // out[c] = sum of the column's segment sums in block order; dots[c] = v[c] * out[c]
@@ -172,9 +246,41 @@ LsNativeResult solve_ls_native(int rows, int cols, const int* rowptr, const int*
     d_bounds.upload(h_bounds.data(), kRowBlocks + 1, s);
     MRB_CUDA(cudaStreamSynchronize(s));
     SegTable seg;
-    build_segments(seg, t_ptr.p, t_row.p, cols, nnz, d_bounds.p, kRowBlocks, 1, s);
+    // flat window table (default); MRB_LS_TMUL=seg selects the per-segment groups instead
+    const bool use_flat = !(std::getenv("MRB_LS_TMUL") && std::string(std::getenv("MRB_LS_TMUL")) == "seg");
+    const int nwords = ceil_div(nnz, 32);
+    DevBuf<unsigned> heads(static_cast<size_t>(nwords) + 1);
+    DevBuf<int> win_first(static_cast<size_t>(nwords) + 1), col_piece_ptr(static_cast<size_t>(cols) + 1);
+    DevBuf<double> piece_sum;
+    int npieces = 0;
+    if (use_flat) {
+        k_flat_init_heads<<<ceil_div(nwords + 1, 256), 256, 0, s>>>(heads.p, nwords);
+        if (cols > 0) k_flat_mark_heads<<<ceil_div(cols, 256), 256, 0, s>>>(t_ptr.p, cols, heads.p);
+        k_flat_popc<<<ceil_div(nwords + 1, 256), 256, 0, s>>>(heads.p, nwords, win_first.p);
+        MRB_LAUNCHED(3);
+        MRB_CUDA(cudaGetLastError());
+        exclusive_scan_i32(win_first.p, win_first.p, static_cast<long long>(nwords) + 1, s);
+        k_flat_col_ptr<<<ceil_div(cols + 1, 256), 256, 0, s>>>(t_ptr.p, cols, heads.p, win_first.p,
+                                                            col_piece_ptr.p);
+        MRB_LAUNCHED(1);
+        MRB_CUDA(cudaGetLastError());
+        MRB_CUDA(cudaMemcpyAsync(&npieces, win_first.p + nwords, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MRB_CUDA(cudaStreamSynchronize(s));
+        piece_sum.alloc(static_cast<size_t>(std::max(npieces, 1)));
+    }
+    if (!use_flat) build_segments(seg, t_ptr.p, t_row.p, cols, nnz, d_bounds.p, kRowBlocks, 1, s);
+    constexpr int kFlatWpw = 4;
     auto tmul = [&](const double* t, const double* v, double* out, double* dd, const CgState* guard) {
         if (cols == 0) return;
+        if (use_flat) {
+            if (nwords > 0)
+                k_csc_flat<kFlatWpw><<<ceil_div(static_cast<long long>(ceil_div(nwords, kFlatWpw)) * 32, 256), 256, 0, s>>>(
+                    heads.p, win_first.p, t_row.p, t_val.p, t, piece_sum.p, nnz, nwords, guard);
+            k_csc_fold_native<<<ceil_div(cols, 256), 256, 0, s>>>(col_piece_ptr.p, piece_sum.p, v, out,
+                                                                dd, cols, guard);
+            MRB_LAUNCHED(2);
+            return;
+        }
         if (seg.nseg > 0) {
             const long long mean_len = nnz / seg.nseg;
             if (mean_len < 24)
