@@ -801,31 +801,6 @@ k_chol_solve(const CholArgs A) {
     }
 }
 
-// Sum of squared training errors, deterministic: per-CTA partials in fixed tree order.
-__global__ void __launch_bounds__(256)
-k_sse_partials(const int* __restrict__ user_ids, const int* __restrict__ item_ids,
-               const double* __restrict__ ratings, const double* __restrict__ uf,
-               const double* __restrict__ itf, int k, int nnz, double* __restrict__ partials) {
-    __shared__ double red[256];
-    double s = 0;
-    for (long long r = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; r < nnz;
-         r += static_cast<long long>(gridDim.x) * 256) {
-        const double* u = uf + static_cast<size_t>(user_ids[r]) * (k + 1);
-        const double* v = itf + static_cast<size_t>(item_ids[r]) * k;
-        double pred = u[k];
-        for (int j = 0; j < k; j++) pred += u[j] * v[j];
-        const double d = pred - ratings[r];
-        s += d * d;
-    }
-    red[threadIdx.x] = s;
-    __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
-}
-
 // Fixed-order sum of n doubles (one CTA): thread t adds elements t, t+1024, ... then a tree.
 __global__ void __launch_bounds__(1024)
 k_sum_fixed(const double* __restrict__ in, int n, double* __restrict__ out) {

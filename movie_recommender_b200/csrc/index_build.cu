@@ -212,7 +212,6 @@ void stable_group_by(const int* d_key, int n, int num_groups, int* d_ptr, int* d
     const int* vin = nullptr;
     // ping-pong so that the LAST pass writes its values into d_idx
     int* kbuf[2] = {key_a.p, key_b.p};
-    int* vbuf[2] = {nullptr, nullptr};
     // values alternate between d_idx and val_b; choose so pass (passes-1) lands in d_idx
     for (int p = 0; p < passes; p++) {
         int* kout = kbuf[p & 1];
@@ -226,7 +225,6 @@ void stable_group_by(const int* d_key, int n, int num_groups, int* d_ptr, int* d
         kin = kout;
         vin = vout;
     }
-    (void)vbuf;
     MRB_CUDA(cudaStreamSynchronize(s));  // temporaries are freed on return
 }
 

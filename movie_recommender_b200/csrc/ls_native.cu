@@ -3,8 +3,9 @@
 // GPU-native summation: the "linear model" path of config 2 (user + movie bias model, 2 non-zeros
 // per row).  Same algorithm and stopping rule as the reference; per CG iteration
 //   t  = A p      CSR, one thread per short row / one warp per long row
-//   Ap = A^T t    through the stable transpose built once by K4 (CSC), one warp per column,
-//                 fused with the per-column partial of p . Ap
+//   Ap = A^T t    through the stable transpose built once by K4 (CSC): one lane per entry in
+//                 32-entry windows (k_csc_flat), then an ordered fold per column fused with
+//                 the per-column partial of p . Ap
 //   x, r, p updates fused with the partial sums of r . r
 // All HBM streaming; algorithmic bytes per iteration (nnz_A = non-zeros):
 //   2*nnz_A*(8+4) + (rows+cols+2)*4 + rows*8 + nnz_A*8 + 7*cols*8.
@@ -186,33 +187,6 @@ k_csc_fold_group(const int* __restrict__ col_piece_ptr, const double* __restrict
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (live && sub == 0) {
-        out[c] = s;
-        if (dots) dots[c] = v ? v[c] * s : 0.0;
-    }
-}
-
-// out[c] = sum over column c of val * t[row]; dots[c] = v[c] * out[c] (v may be null)
-__global__ void __launch_bounds__(256)
-k_csc_tmul_warp(const int* __restrict__ t_ptr, const int* __restrict__ t_row,
-                const double* __restrict__ t_val, const double* __restrict__ t,
-                const double* __restrict__ v, double* __restrict__ out, double* __restrict__ dots,
-                int cols, const CgState* __restrict__ guard) {
-    if (guard && guard->done) return;
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= cols) return;
-    const int lane = threadIdx.x & 31;
-    const int beg = t_ptr[c], end = t_ptr[c + 1];
-    double s0 = 0, s1 = 0;
-    int e = beg + lane;
-    for (; e + 32 < end; e += 64) {
-        s0 += t_val[e] * t[t_row[e]];
-        s1 += t_val[e + 32] * t[t_row[e + 32]];
-    }
-    if (e < end) s0 += t_val[e] * t[t_row[e]];
-    double s = s0 + s1;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) {
         out[c] = s;
         if (dots) dots[c] = v ? v[c] * s : 0.0;
     }
