@@ -185,3 +185,73 @@ def e2e_steps(problem, k, num_users, num_items, rank, world, steps, exchange="p2
         if step > 0:
             times.append(float(dt.item()))
     return sum(times) / len(times), uf_host, itf_host
+
+
+# ----------------------------------------------------------------------------------------------
+# Similarity over several GPUs: query movies are independent, so the split
+# is by contiguous query block with the whole catalogue replicated on every rank; the only
+# exchange is the final gather of the per-block results.  The reference splits the same job the
+# same way over its worker processes (movie_lens_data_proc.py:127-150 split_range_and_send,
+# :657-700 _find_similar_movies, :264-279 update_var_into_dict).
+# ----------------------------------------------------------------------------------------------
+def query_blocks(num_queries, world):
+    """bounds[0..world]: contiguous query blocks whose sizes differ by at most one."""
+    return [num_queries * r // world for r in range(world + 1)]
+
+
+def _gather_rows(local, bounds, rank, world, fill):
+    """All-gather of per-rank row blocks of different heights (padded to the tallest block):
+    every rank returns the stacked (bounds[-1], cols) array."""
+    import torch
+    import torch.distributed as dist
+    tallest = max(bounds[r + 1] - bounds[r] for r in range(world))
+    device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" \
+        else torch.device("cpu")
+    padded = np.full((tallest,) + local.shape[1:], fill, dtype=local.dtype)
+    padded[:local.shape[0]] = local
+    mine = torch.from_numpy(padded).to(device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return np.concatenate([parts[r][:bounds[r + 1] - bounds[r]].cpu().numpy() for r in range(world)])
+
+
+def sharded_factor_cosine_topk(item_factors, topk, rank, world, num_factors=None, compute=None):
+    """Config 4 on ``world`` GPUs: this rank computes the top-``topk`` of its query block
+    (``similarity.factor_cosine_topk(..., q_lo, q_hi)``), then the ``(N / world) x topk`` id and
+    score blocks are all-gathered.  Returns ``(ids int32[N, topk], scores f64[N, topk])`` on every
+    rank; ``compute`` replaces the GPU call (host-logic tests)."""
+    M = np.ascontiguousarray(item_factors, dtype=np.float64)
+    if M.ndim == 1:
+        M = M.reshape(-1, num_factors)
+    bounds = query_blocks(M.shape[0], world)
+    if compute is None:
+        from . import similarity
+
+        def compute(q_lo, q_hi):
+            ids, scores, _ = similarity.factor_cosine_topk(M, topk=topk, q_lo=q_lo, q_hi=q_hi)
+            return ids, scores
+    ids, scores = compute(bounds[rank], bounds[rank + 1])
+    if world == 1:
+        return ids, scores
+    return (_gather_rows(np.ascontiguousarray(ids, dtype=np.int32), bounds, rank, world, -1),
+            _gather_rows(np.ascontiguousarray(scores, dtype=np.float64), bounds, rank, world, 0.0))
+
+
+def sharded_build_similar_movies(finder, rank, world, num_results=20, build=None):
+    """The reference's similar_movies.bin job on ``world`` GPUs: every rank holds the whole
+    ``SimilarMovieFinder`` and builds ``{movie_id: (similar movie ids)}`` for its block of the
+    movie list; the dictionaries are merged on every rank in rank order, as the reference merges
+    its workers' (movie_lens_data_proc.py:264-279).  ``build`` replaces ``finder.build``."""
+    import torch.distributed as dist
+    n = len(finder._movie_ids) if build is None else finder
+    bounds = query_blocks(n, world)
+    run = finder.build if build is None else build
+    mine = run(num_results=num_results, start=bounds[rank], length=bounds[rank + 1] - bounds[rank])
+    if world == 1:
+        return mine
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    merged = {}
+    for part in parts:
+        merged.update(part)
+    return merged

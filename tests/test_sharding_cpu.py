@@ -60,3 +60,55 @@ def test_shard_ranges_edge_cases():
     empty = np.zeros(4, dtype=np.int32)                       # three rows, no ratings
     assert list(cpp_ls.shard_ranges(empty, 2))[0] == 0
     assert list(cpp_ls.shard_ranges(np.array([0], dtype=np.int32), 4)) == [0, 0, 0, 0, 0]
+
+
+SIM_WORKER = r'''
+import sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, %r)
+from movie_recommender_b200 import sharded
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n, topk = 101, 7                       # not divisible by the world size: blocks of unequal height
+M = np.random.default_rng(3).standard_normal((n, 5))
+def reference_rows(lo, hi):            # a NumPy stand-in for the GPU call, same contract
+    H = M / np.linalg.norm(M, axis=1, keepdims=True)
+    S = np.array([[float(np.dot(H[q], H[j])) for j in range(n)] for q in range(lo, hi)])   # per-pair
+    # dots: a BLAS GEMM rounds a row block differently from the full matrix
+    S[np.arange(hi - lo), np.arange(lo, hi)] = -np.inf
+    ids = np.argsort(-S, axis=1, kind="stable")[:, :topk].astype(np.int32)
+    return ids, np.take_along_axis(S, ids, axis=1)
+calls = []
+def compute(lo, hi):
+    calls.append((lo, hi))
+    return reference_rows(lo, hi)
+ids, scores = sharded.sharded_factor_cosine_topk(M, topk, rank, world, compute=compute)
+b = sharded.query_blocks(n, world)
+assert calls == [(b[rank], b[rank + 1])] and b[0] == 0 and b[-1] == n
+full_ids, full_scores = reference_rows(0, n)
+assert ids.shape == (n, topk) and np.array_equal(ids, full_ids)
+assert np.array_equal(scores.view(np.uint64), full_scores.view(np.uint64))
+# the dictionary job: blocks of the movie list, merged on every rank
+def build(num_results, start, length):
+    return {1000 + q: tuple(range(q, q + num_results)) for q in range(start, start + length) if q %% 5}
+merged = sharded.sharded_build_similar_movies(n, rank, world, num_results=3, build=build)
+assert merged == build(3, 0, n)
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_similarity_query_blocks_world2_gloo(tmp_path):
+    from movie_recommender_b200 import sharded
+    assert sharded.query_blocks(10, 4) == [0, 2, 5, 7, 10]
+    assert sharded.query_blocks(0, 3) == [0, 0, 0, 0]
+    script = tmp_path / "sim_worker.py"
+    script.write_text(SIM_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29519")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+                          "29519", str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2
