@@ -176,6 +176,11 @@ class SimilarMovieFinder:
         if buff < 0: buff = 0
         return similarity * (1.0 + buff), n, similarity
 
+    @property
+    def num_movies(self):
+        """Length of the movie list (the range ``build`` and the multi-GPU split index)."""
+        return self._n_movies
+
     def find_movie_index(self, movie_id: int):
         """Return the "movie_ratings" list index for movie_id, -1 if absent (:136-147)."""
         hit = numpy.flatnonzero(self._movie_ids == movie_id)

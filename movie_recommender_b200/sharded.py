@@ -237,16 +237,16 @@ def sharded_factor_cosine_topk(item_factors, topk, rank, world, num_factors=None
             _gather_rows(np.ascontiguousarray(scores, dtype=np.float64), bounds, rank, world, 0.0))
 
 
-def sharded_build_similar_movies(finder, rank, world, num_results=20, build=None):
+def sharded_build_similar_movies(finder, rank, world, num_results=20):
     """The reference's similar_movies.bin job on ``world`` GPUs: every rank holds the whole
-    ``SimilarMovieFinder`` and builds ``{movie_id: (similar movie ids)}`` for its block of the
-    movie list; the dictionaries are merged on every rank in rank order, as the reference merges
-    its workers' (movie_lens_data_proc.py:264-279).  ``build`` replaces ``finder.build``."""
+    ``SimilarMovieFinder`` (anything with ``num_movies`` and ``build(num_results, start, length)``)
+    and builds ``{movie_id: (similar movie ids)}`` for its block of the movie list; the
+    dictionaries are merged on every rank in rank order, as the reference merges its workers'
+    (movie_lens_data_proc.py:264-279)."""
     import torch.distributed as dist
-    n = len(finder._movie_ids) if build is None else finder
-    bounds = query_blocks(n, world)
-    run = finder.build if build is None else build
-    mine = run(num_results=num_results, start=bounds[rank], length=bounds[rank + 1] - bounds[rank])
+    bounds = query_blocks(finder.num_movies, world)
+    mine = finder.build(num_results=num_results, start=bounds[rank],
+                        length=bounds[rank + 1] - bounds[rank])
     if world == 1:
         return mine
     parts = [None] * world

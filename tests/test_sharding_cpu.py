@@ -90,10 +90,12 @@ full_ids, full_scores = reference_rows(0, n)
 assert ids.shape == (n, topk) and np.array_equal(ids, full_ids)
 assert np.array_equal(scores.view(np.uint64), full_scores.view(np.uint64))
 # the dictionary job: blocks of the movie list, merged on every rank
-def build(num_results, start, length):
-    return {1000 + q: tuple(range(q, q + num_results)) for q in range(start, start + length) if q %% 5}
-merged = sharded.sharded_build_similar_movies(n, rank, world, num_results=3, build=build)
-assert merged == build(3, 0, n)
+class Finder:                          # the two members the split needs
+    num_movies = n
+    def build(self, num_results, start, length):
+        return {1000 + q: tuple(range(q, q + num_results)) for q in range(start, start + length) if q %% 5}
+merged = sharded.sharded_build_similar_movies(Finder(), rank, world, num_results=3)
+assert merged == Finder().build(3, 0, n)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
