@@ -1,4 +1,4 @@
-// Gram-block ALS (algorithm 4: gathered Gram + in-shared-memory Cholesky; algorithm 3: the
+// Gram-block ALS (algorithm 4: gathered Gram + register-resident Cholesky; algorithm 3: the
 // reference's global-scalar CG run on the stored Gram blocks).  See als.cuh for the data layout.
 //
 // K1 "gather-Gram".  Every row r of the reference's materialised user_A touches only user u's
@@ -14,10 +14,12 @@
 // The fragment for 8-wide tile t of ratings q..q+3 is the same register whether it is used as
 // the A operand (row.k) or the B operand (k.col), so one set of loads feeds both.
 //
-// K2b "Cholesky".  The augmented matrix is staged in shared memory; its Cholesky factor's last
-// row is y = L^-1 g, so forward substitution is free and only L^T x = y remains.  lambda = 0 as
-// in the reference: unknowns the data do not determine (pivot <= 1e-12 of the original
-// diagonal) keep their previous value (the solve is for the correction to the warm start).
+// K2b "Cholesky".  The augmented matrix stays in the accumulator fragments (no shared memory,
+// see gram_solve); its Cholesky factor's last row is y = L^-1 g, so forward substitution is free
+// and only L^T x = y remains.  lambda = 0 as in the reference: unknowns the data do not
+// determine (pivot <= 1e-12 of the original diagonal) keep their previous value (the solve is
+// for the correction to the warm start).  Ranks above 54 take the block-wise path further down
+// (Gram blocks to HBM, one shared-memory Cholesky per owner).
 //
 // Heavy owners are cut into segments of SEG ratings processed by different warps; the partial
 // Gram matrices are summed in SEGMENT ORDER by whichever warp finishes last, so the result does
