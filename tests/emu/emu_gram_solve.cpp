@@ -1,0 +1,50 @@
+// Runs the device function mrb::gram_solve<M8> (csrc/gram_solve.cuh) on an emulated warp.
+// TEST INFRASTRUCTURE ONLY.  Build: tests/emu/Makefile.
+#define MRB_HOST_EMU 1
+#include "gram_solve.cuh"
+
+#include <thread>
+#include <vector>
+
+namespace {
+template <int M8>
+void run(int n, const double* aug, int ld, double* x, double* sse) {
+    constexpr int ST = M8 * (M8 + 1) / 2;
+    warp_emu::Warp warp;
+    mrb::GramArgs args{};
+    std::vector<std::thread> lanes;
+    for (int lane = 0; lane < 32; lane++)
+        lanes.emplace_back([&, lane] {
+            warp_emu::t_warp = &warp;
+            warp_emu::t_lane = lane;
+            const int p = lane >> 2, q = lane & 3;
+            double acc[ST][2];
+            // the accumulator fragment layout of k_gram: lane (p, q) holds rows 8 ti + p,
+            // columns 8 tj + 2q, + 1 of every lower-triangular tile
+            for (int ti = 0; ti < M8; ti++)
+                for (int tj = 0; tj <= ti; tj++)
+                    for (int h = 0; h < 2; h++)
+                        acc[mrb::TI(ti, tj)][h] = aug[(8 * ti + p) * ld + 8 * tj + 2 * q + h];
+            mrb::gram_solve<M8>(acc, n, x, sse, lane, args, 0);
+        });
+    for (auto& t : lanes) t.join();
+}
+}  // namespace
+
+// aug: row-major (8 m8) x ld matrix holding the augmented symmetric matrix [G g; g^T s] of order
+// n + 1 (lower triangle used, zero beyond); x: n values, previous factors in, solution out;
+// sse: receives s - (residual bookkeeping) = sum of squared residuals at the solution.
+extern "C" int emu_gram_solve(int m8, int n, const double* aug, int ld, double* x, double* sse) {
+    if (n + 1 > 8 * m8 || n + 1 <= 8 * (m8 - 1)) return -2;   // the rhs must sit in the last tile row
+    switch (m8) {
+        case 1: run<1>(n, aug, ld, x, sse); break;
+        case 2: run<2>(n, aug, ld, x, sse); break;
+        case 3: run<3>(n, aug, ld, x, sse); break;
+        case 4: run<4>(n, aug, ld, x, sse); break;
+        case 5: run<5>(n, aug, ld, x, sse); break;
+        case 6: run<6>(n, aug, ld, x, sse); break;
+        case 7: run<7>(n, aug, ld, x, sse); break;
+        default: return -2;
+    }
+    return 0;
+}
