@@ -49,6 +49,9 @@ constexpr int GRAM_WARPS = 4;      // warps per CTA
 #ifndef GRAM_DEFAULT_ORDER
 #define GRAM_DEFAULT_ORDER 0
 #endif
+#ifndef GRAM_SOLVE_VARIANT
+#define GRAM_SOLVE_VARIANT 0       // 1: block-of-four pivot candidate (gram_solve.cuh), A/B builds only
+#endif
 
 // Element j of the augmented row [a; b] AS FETCHED: no arithmetic on a value that has just been
 // requested from memory (a dependent instruction right behind the load would stall the warp
@@ -295,7 +298,7 @@ k_gram(const GramArgs A) {
             if (acc[0][0] == 1.2345e300) A.x[0] = acc[ST - 1][1];   // keep the accumulation alive
             continue;
         }
-        gram_solve<M8>(acc, n, A.x + static_cast<size_t>(wi.owner) * n,
+        gram_solve<M8, GRAM_SOLVE_VARIANT>(acc, n, A.x + static_cast<size_t>(wi.owner) * n,
                        A.sse_out ? A.sse_out + wi.owner : nullptr, lane, A,
                        static_cast<size_t>(wi.owner) * n);
     }

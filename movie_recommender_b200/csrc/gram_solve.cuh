@@ -107,7 +107,7 @@ MRB_DEVICE_INLINE double xor_sum_q(double v) {   // sum over the 4 lanes sharing
 // pivot falls below 1e-12 of the original diagonal get delta = 0 (they keep their previous value,
 // as they do under the reference's warm-started CG), the others are solved consistently.
 // ------------------------------------------------------------------------------------------
-template <int M8>
+template <int M8, int VARIANT = 0>
 MRB_DEVICE_INLINE void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], int n,
                                            double* __restrict__ xo, double* __restrict__ sse_slot,
                                            int lane, const GramArgs& A, size_t row_offset) {
@@ -179,78 +179,179 @@ MRB_DEVICE_INLINE void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], int n,
     for (int t = 0; t < M8; t++) invd[t] = 0;
     double corner = 0;
 
-    // The whole factorisation is branch-free per lane (selects on multipliers, never divergent
-    // control flow around a shuffle) and keeps the pivot columns UNSCALED inside a tile column:
-    //   X[p][c2] -= X[p][c] * (D[c2][c] / d_c)      for the 8 pivots c of the tile column,
-    // then one scaling of the finished panel by 1/sqrt(d_c) per column.  Per pivot and tile that
-    // is one shuffle and two DFMAs.
+    if constexpr (VARIANT == 1) {
+        // ---- CANDIDATE (not the default; developed on the emulated warp, tests/emu): pivots in
+        // blocks of FOUR = the k of mma.m8n8k4.  Per block: the 4x4 diagonal block S and its four
+        // thresholds are broadcast to every lane; every lane factors S = L4 L4^T and forms
+        // W = L4^-T in registers (no shuffle inside the dependent chain; a skipped pivot has
+        // r = 0, which zeroes its column of L4 and of W); the block's columns of every tile of
+        // the tile column become P W with one DMMA (B operand picked from the lane's own W,
+        // placed in columns 4h .. 4h+3); every trailing update, the right half of the same tile
+        // column included (masked B operand), is a rank-4 DMMA.
 #pragma unroll
-    for (int tk = 0; tk < M8; tk++) {
-        const int D = TI(tk, tk);
-        // the 8 pivot columns, rolled in pairs (cp = c >> 1 at run time, slot j = c & 1 static):
-        // 4x less code than a full unroll -- the epilogue was instruction-cache bound
-#pragma unroll 1
-        for (int cp = 0; cp < 4; cp++) {
+        for (int tk = 0; tk < M8; tk++) {
+            const int D = TI(tk, tk);
 #pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int c = 2 * cp + j;
-                // warp-uniform: only the last tile column has non-pivot columns
-                if (tk < M8 - 1 || c < pr) {
-                    // the owner lane (p = c, q = cp) holds d = D[c][c] in slot j and its threshold
-                    // in thr[tk]; every lane runs the reciprocal square root on its own value
-                    const double dv = acc[D][j];
-                    const bool ok = dv > thr[tk] && thr[tk] > 1e-290;   // false for NaN
-                    const double r = shfl_double(ok ? fast_rsqrt(dv) : 0.0, c * 4 + cp);
-                    if (p == c) invd[tk] = r;
-                    if (c < 7) {
-                        const double inv_d = r * r;
-                        // D[c2][c] / d for this lane's two columns c2 = 2q, 2q+1 (0 for c2 <= c)
-                        const double m0 = shfl_double(dv, (2 * q) * 4 + cp);
-                        const double m1 = shfl_double(dv, (2 * q + 1) * 4 + cp);
-                        const double f0 = q > cp ? m0 * inv_d : 0.0;
-                        const double f1 = (j == 0 ? q >= cp : q > cp) ? m1 * inv_d : 0.0;
+            for (int h = 0; h < 2; h++) {
+                // warp-uniform: in the last tile column only the blocks up to the one holding
+                // index n (fragment row/column pr) exist
+                if (tk == M8 - 1 && 4 * h > pr) continue;
+                const int l0 = (4 * h) * 4 + 2 * h;          // lane (4h, 2h): row 4h, columns 4h, 4h+1
+                const double S00 = shfl_double(acc[D][0], l0);
+                const double S10 = shfl_double(acc[D][0], l0 + 4), S11 = shfl_double(acc[D][1], l0 + 4);
+                const double S20 = shfl_double(acc[D][0], l0 + 8), S21 = shfl_double(acc[D][1], l0 + 8);
+                const double S22 = shfl_double(acc[D][0], l0 + 9);
+                const double S30 = shfl_double(acc[D][0], l0 + 12), S31 = shfl_double(acc[D][1], l0 + 12);
+                const double S32 = shfl_double(acc[D][0], l0 + 13), S33 = shfl_double(acc[D][1], l0 + 13);
+                // threshold of column c = 4h + j sits on lane (c, c >> 1)
+                const double t0 = shfl_double(thr[tk], (4 * h + 0) * 4 + 2 * h);
+                const double t1 = shfl_double(thr[tk], (4 * h + 1) * 4 + 2 * h);
+                const double t2 = shfl_double(thr[tk], (4 * h + 2) * 4 + 2 * h + 1);
+                const double t3 = shfl_double(thr[tk], (4 * h + 3) * 4 + 2 * h + 1);
+                const bool last = tk == M8 - 1;
+                // local factorisation, identical on every lane
+                const double d0 = S00;
+                const bool ok0 = (!last || 4 * h + 0 < pr) && d0 > t0 && t0 > 1e-290;
+                const double r0 = ok0 ? fast_rsqrt(d0) : 0.0;
+                const double L10 = S10 * r0, L20 = S20 * r0, L30 = S30 * r0;
+                const double d1 = fma(-L10, L10, S11);
+                const bool ok1 = (!last || 4 * h + 1 < pr) && d1 > t1 && t1 > 1e-290;
+                const double r1 = ok1 ? fast_rsqrt(d1) : 0.0;
+                const double L21 = fma(-L20, L10, S21) * r1, L31 = fma(-L30, L10, S31) * r1;
+                const double d2 = fma(-L21, L21, fma(-L20, L20, S22));
+                const bool ok2 = (!last || 4 * h + 2 < pr) && d2 > t2 && t2 > 1e-290;
+                const double r2 = ok2 ? fast_rsqrt(d2) : 0.0;
+                const double L32 = fma(-L31, L21, fma(-L30, L20, S32)) * r2;
+                const double d3 = fma(-L32, L32, fma(-L31, L31, fma(-L30, L30, S33)));
+                const bool ok3 = (!last || 4 * h + 3 < pr) && d3 > t3 && t3 > 1e-290;
+                const double r3 = ok3 ? fast_rsqrt(d3) : 0.0;
+                if (last && (pr >> 2) == h) {
+                    const int j = pr & 3;
+                    corner = j == 0 ? d0 : (j == 1 ? d1 : (j == 2 ? d2 : d3));
+                }
+                // W = L4^-T, upper triangular: W[:,j] = (e_j - sum_{k<j} W[:,k] L4[j][k]) r_j
+                const double W00 = r0;
+                const double W01 = -(W00 * L10) * r1, W11 = r1;
+                const double W02 = -fma(W01, L21, W00 * L20) * r2, W12 = -(W11 * L21) * r2, W22 = r2;
+                const double W03 = -fma(W02, L32, fma(W01, L31, W00 * L30)) * r3;
+                const double W13 = -fma(W12, L32, W11 * L31) * r3, W23 = -(W22 * L32) * r3, W33 = r3;
+                // B operand of P W: lane (p, q) holds B[q][p] = W[q][p - 4h] inside the block
+                const int jj = p & 3;
+                const double w_q0 = jj == 0 ? W00 : (jj == 1 ? W01 : (jj == 2 ? W02 : W03));
+                const double w_q1 = jj == 0 ? 0.0 : (jj == 1 ? W11 : (jj == 2 ? W12 : W13));
+                const double w_q2 = jj < 2 ? 0.0 : (jj == 2 ? W22 : W23);
+                const double w_q3 = jj == 3 ? W33 : 0.0;
+                double bw = q == 0 ? w_q0 : (q == 1 ? w_q1 : (q == 2 ? w_q2 : w_q3));
+                const bool in_rows = (p >> 2) == h;
+                bw = in_rows ? bw : 0.0;
+                if (in_rows) invd[tk] = jj == 0 ? r0 : (jj == 1 ? r1 : (jj == 2 ? r2 : r3));
+                // the block's columns of the tile column: P <- P W; A fragments of the result
+                const int src = p * 4 + 2 * h + (q >> 1);       // lane holding X[p][4h + q]
+                const bool in_cols = (q >> 1) == h;
+                double ax[M8];
 #pragma unroll
-                        for (int ti = tk; ti < M8; ti++) {
-                            const int X = TI(ti, tk);
-                            const double xrc = shfl_double(acc[X][j], p * 4 + cp);   // X[p][c]
-                            acc[X][0] = fma(-xrc, f0, acc[X][0]);
-                            acc[X][1] = fma(-xrc, f1, acc[X][1]);
+                for (int ti = tk; ti < M8; ti++) {
+                    const int X = TI(ti, tk);
+                    const double v0 = shfl_double(acc[X][0], src);
+                    const double v1 = shfl_double(acc[X][1], src);
+                    const double a_old = (q & 1) ? v1 : v0;
+                    double c0 = in_cols ? 0.0 : acc[X][0], c1 = in_cols ? 0.0 : acc[X][1];
+                    dmma884(c0, c1, a_old, bw);
+                    acc[X][0] = c0;
+                    acc[X][1] = c1;
+                    const double n0 = shfl_double(c0, src);
+                    const double n1 = shfl_double(c1, src);
+                    ax[ti] = (q & 1) ? n1 : n0;                  // L(ti,tk)[p][4h + q]
+                }
+                if (h == 0) {
+                    // right half of the same tile column: X[:, 4..7] -= L(ti)[:, 0..3] Ld[4..7, 0..3]^T
+                    const double bmask = (p >> 2) == 1 ? ax[tk] : 0.0;
+#pragma unroll
+                    for (int ti = tk; ti < M8; ti++)
+                        dmma884(acc[TI(ti, tk)][0], acc[TI(ti, tk)][1], -ax[ti], bmask);
+                }
+#pragma unroll
+                for (int ti = tk + 1; ti < M8; ti++)
+#pragma unroll
+                    for (int tj = tk + 1; tj <= ti; tj++)
+                        dmma884(acc[TI(ti, tj)][0], acc[TI(ti, tj)][1], -ax[ti], ax[tj]);
+            }
+        }
+    } else {
+        // The whole factorisation is branch-free per lane (selects on multipliers, never divergent
+        // control flow around a shuffle) and keeps the pivot columns UNSCALED inside a tile column:
+        //   X[p][c2] -= X[p][c] * (D[c2][c] / d_c)      for the 8 pivots c of the tile column,
+        // then one scaling of the finished panel by 1/sqrt(d_c) per column.  Per pivot and tile that
+        // is one shuffle and two DFMAs.
+    #pragma unroll
+        for (int tk = 0; tk < M8; tk++) {
+            const int D = TI(tk, tk);
+            // the 8 pivot columns, rolled in pairs (cp = c >> 1 at run time, slot j = c & 1 static):
+            // 4x less code than a full unroll -- the epilogue was instruction-cache bound
+    #pragma unroll 1
+            for (int cp = 0; cp < 4; cp++) {
+    #pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int c = 2 * cp + j;
+                    // warp-uniform: only the last tile column has non-pivot columns
+                    if (tk < M8 - 1 || c < pr) {
+                        // the owner lane (p = c, q = cp) holds d = D[c][c] in slot j and its threshold
+                        // in thr[tk]; every lane runs the reciprocal square root on its own value
+                        const double dv = acc[D][j];
+                        const bool ok = dv > thr[tk] && thr[tk] > 1e-290;   // false for NaN
+                        const double r = shfl_double(ok ? fast_rsqrt(dv) : 0.0, c * 4 + cp);
+                        if (p == c) invd[tk] = r;
+                        if (c < 7) {
+                            const double inv_d = r * r;
+                            // D[c2][c] / d for this lane's two columns c2 = 2q, 2q+1 (0 for c2 <= c)
+                            const double m0 = shfl_double(dv, (2 * q) * 4 + cp);
+                            const double m1 = shfl_double(dv, (2 * q + 1) * 4 + cp);
+                            const double f0 = q > cp ? m0 * inv_d : 0.0;
+                            const double f1 = (j == 0 ? q >= cp : q > cp) ? m1 * inv_d : 0.0;
+    #pragma unroll
+                            for (int ti = tk; ti < M8; ti++) {
+                                const int X = TI(ti, tk);
+                                const double xrc = shfl_double(acc[X][j], p * 4 + cp);   // X[p][c]
+                                acc[X][0] = fma(-xrc, f0, acc[X][0]);
+                                acc[X][1] = fma(-xrc, f1, acc[X][1]);
+                            }
                         }
                     }
                 }
             }
-        }
-        if (tk == M8 - 1) corner = (pr & 1) ? acc[D][1] : acc[D][0];   // valid on lane (pr, pr>>1)
-        {
-            // L = X diag(1/sqrt(d)); skipped pivots and the non-pivot columns become 0
-            const double r0 = shfl_double(invd[tk], (2 * q) * 4);
-            const double r1 = shfl_double(invd[tk], (2 * q + 1) * 4);
-#pragma unroll
-            for (int ti = tk; ti < M8; ti++) {
-                acc[TI(ti, tk)][0] *= r0;
-                acc[TI(ti, tk)][1] *= r1;
+            if (tk == M8 - 1) corner = (pr & 1) ? acc[D][1] : acc[D][0];   // valid on lane (pr, pr>>1)
+            {
+                // L = X diag(1/sqrt(d)); skipped pivots and the non-pivot columns become 0
+                const double r0 = shfl_double(invd[tk], (2 * q) * 4);
+                const double r1 = shfl_double(invd[tk], (2 * q + 1) * 4);
+    #pragma unroll
+                for (int ti = tk; ti < M8; ti++) {
+                    acc[TI(ti, tk)][0] *= r0;
+                    acc[TI(ti, tk)][1] *= r1;
+                }
+            }
+            if (tk < M8 - 1) {
+                // trailing update on the tensor cores
+                double ax[M8][2];
+    #pragma unroll
+                for (int ti = tk + 1; ti < M8; ti++)
+    #pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int src = p * 4 + 2 * h + (q >> 1);
+                        const double v0 = shfl_double(acc[TI(ti, tk)][0], src);
+                        const double v1 = shfl_double(acc[TI(ti, tk)][1], src);
+                        ax[ti][h] = (q & 1) ? v1 : v0;   // L(ti,tk)[p][4h+q]
+                    }
+    #pragma unroll
+                for (int ti = tk + 1; ti < M8; ti++)
+    #pragma unroll
+                    for (int tj = tk + 1; tj <= ti; tj++) {
+                        dmma884(acc[TI(ti, tj)][0], acc[TI(ti, tj)][1], -ax[ti][0], ax[tj][0]);
+                        dmma884(acc[TI(ti, tj)][0], acc[TI(ti, tj)][1], -ax[ti][1], ax[tj][1]);
+                    }
             }
         }
-        if (tk < M8 - 1) {
-            // trailing update on the tensor cores
-            double ax[M8][2];
-#pragma unroll
-            for (int ti = tk + 1; ti < M8; ti++)
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int src = p * 4 + 2 * h + (q >> 1);
-                    const double v0 = shfl_double(acc[TI(ti, tk)][0], src);
-                    const double v1 = shfl_double(acc[TI(ti, tk)][1], src);
-                    ax[ti][h] = (q & 1) ? v1 : v0;   // L(ti,tk)[p][4h+q]
-                }
-#pragma unroll
-            for (int ti = tk + 1; ti < M8; ti++)
-#pragma unroll
-                for (int tj = tk + 1; tj <= ti; tj++) {
-                    dmma884(acc[TI(ti, tj)][0], acc[TI(ti, tj)][1], -ax[ti][0], ax[tj][0]);
-                    dmma884(acc[TI(ti, tj)][0], acc[TI(ti, tj)][1], -ax[ti][1], ax[tj][1]);
-                }
-        }
+
     }
 
     // ---- residual: corner - x0.(g + g')  ==  sum (b - a.x)^2 at the solution

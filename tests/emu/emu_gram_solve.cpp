@@ -7,7 +7,7 @@
 #include <vector>
 
 namespace {
-template <int M8>
+template <int M8, int VARIANT>
 void run(int n, const double* aug, int ld, double* x, double* sse) {
     constexpr int ST = M8 * (M8 + 1) / 2;
     warp_emu::Warp warp;
@@ -25,7 +25,7 @@ void run(int n, const double* aug, int ld, double* x, double* sse) {
                 for (int tj = 0; tj <= ti; tj++)
                     for (int h = 0; h < 2; h++)
                         acc[mrb::TI(ti, tj)][h] = aug[(8 * ti + p) * ld + 8 * tj + 2 * q + h];
-            mrb::gram_solve<M8>(acc, n, x, sse, lane, args, 0);
+            mrb::gram_solve<M8, VARIANT>(acc, n, x, sse, lane, args, 0);
         });
     for (auto& t : lanes) t.join();
 }
@@ -34,17 +34,26 @@ void run(int n, const double* aug, int ld, double* x, double* sse) {
 // aug: row-major (8 m8) x ld matrix holding the augmented symmetric matrix [G g; g^T s] of order
 // n + 1 (lower triangle used, zero beyond); x: n values, previous factors in, solution out;
 // sse: receives s - (residual bookkeeping) = sum of squared residuals at the solution.
-extern "C" int emu_gram_solve(int m8, int n, const double* aug, int ld, double* x, double* sse) {
+namespace {
+template <int VARIANT>
+int dispatch(int m8, int n, const double* aug, int ld, double* x, double* sse) {
     if (n + 1 > 8 * m8 || n + 1 <= 8 * (m8 - 1)) return -2;   // the rhs must sit in the last tile row
     switch (m8) {
-        case 1: run<1>(n, aug, ld, x, sse); break;
-        case 2: run<2>(n, aug, ld, x, sse); break;
-        case 3: run<3>(n, aug, ld, x, sse); break;
-        case 4: run<4>(n, aug, ld, x, sse); break;
-        case 5: run<5>(n, aug, ld, x, sse); break;
-        case 6: run<6>(n, aug, ld, x, sse); break;
-        case 7: run<7>(n, aug, ld, x, sse); break;
+        case 1: run<1, VARIANT>(n, aug, ld, x, sse); break;
+        case 2: run<2, VARIANT>(n, aug, ld, x, sse); break;
+        case 3: run<3, VARIANT>(n, aug, ld, x, sse); break;
+        case 4: run<4, VARIANT>(n, aug, ld, x, sse); break;
+        case 5: run<5, VARIANT>(n, aug, ld, x, sse); break;
+        case 6: run<6, VARIANT>(n, aug, ld, x, sse); break;
+        case 7: run<7, VARIANT>(n, aug, ld, x, sse); break;
         default: return -2;
     }
     return 0;
+}
+}  // namespace
+
+// variant 0: the solve the kernel uses; variant 1: the block-of-four candidate
+extern "C" int emu_gram_solve(int variant, int m8, int n, const double* aug, int ld, double* x,
+                              double* sse) {
+    return variant == 0 ? dispatch<0>(m8, n, aug, ld, x, sse) : dispatch<1>(m8, n, aug, ld, x, sse);
 }

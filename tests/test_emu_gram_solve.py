@@ -15,13 +15,14 @@ from conftest import ROOT
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 
 
-@pytest.fixture(scope="module")
-def emu():
+@pytest.fixture(scope="module", params=[0, 1], ids=["kernel", "block4-candidate"])
+def emu(request):
+    variant = request.param
     subprocess.run(["make", "-C", EMU_DIR], check=True, capture_output=True)
     lib = ctypes.CDLL(os.path.join(EMU_DIR, "libemu_gram.so"))
     D = ctypes.POINTER(ctypes.c_double)
     lib.emu_gram_solve.restype = ctypes.c_int
-    lib.emu_gram_solve.argtypes = [ctypes.c_int, ctypes.c_int, D, ctypes.c_int, D, D]
+    lib.emu_gram_solve.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, D, ctypes.c_int, D, D]
 
     def solve(A, b, x0):
         """A: (ratings, n) rows of the owner's least-squares system, b: ratings -> (x, sse)."""
@@ -33,7 +34,8 @@ def emu():
         aug[:n + 1, :n + 1] = Ab.T @ Ab            # [G g; g^T s]
         x = np.array(x0, dtype=np.float64)
         sse = ctypes.c_double(np.nan)
-        rc = lib.emu_gram_solve(m8, n, aug.ctypes.data_as(D), ld, x.ctypes.data_as(D), ctypes.byref(sse))
+        rc = lib.emu_gram_solve(variant, m8, n, aug.ctypes.data_as(D), ld, x.ctypes.data_as(D),
+                                ctypes.byref(sse))
         assert rc == 0
         return x, sse.value
     return solve
