@@ -60,6 +60,12 @@ template <typename T>
 inline T __shfl_sync(unsigned, T v, int src) { return warp_emu::exchange(v, src); }
 template <typename T>
 inline T __shfl_xor_sync(unsigned, T v, int mask) { return warp_emu::exchange(v, warp_emu::t_lane ^ mask); }
+template <typename T>
+inline T __shfl_up_sync(unsigned, T v, int delta) {      // lanes below delta keep their own value
+    return warp_emu::exchange(v, warp_emu::t_lane >= delta ? warp_emu::t_lane - delta : warp_emu::t_lane);
+}
+inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
 
 namespace mrb {
 inline double shfl_double(double v, int src) { return warp_emu::exchange(v, src); }
