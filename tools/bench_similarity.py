@@ -9,6 +9,7 @@ logic is covered by tests/test_sharding_cpu.py on gloo, it has not run on GPUs y
 import argparse, json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
 from movie_recommender_b200 import similarity
 
 ap = argparse.ArgumentParser()
