@@ -154,15 +154,18 @@ MRB_API void mrb_als_destroy(mrb_als_problem* p);
 
 /* ------------------------------------------------------------------------------------------
  * 5. Extensions: multi-GPU, one process per GPU.
- *    Users, then movies, are row-partitioned in nnz-balanced contiguous ranges; each rank holds
- *    full replicas of both factor matrices.  The exact-solve kernel (algorithm 4) stores every
- *    solved row into all replicas through NVLink peer pointers, i.e. the all-gather of the factor
- *    shards is fused into the producing kernel; the caller only needs a stream-ordered barrier
- *    between half-sweeps (bench: a one-element NCCL all-reduce).
+ *    Users, then movies, are row-partitioned (degree-sorted rows dealt over the ranks, or
+ *    nnz-balanced contiguous ranges); each rank holds full replicas of both factor matrices.
+ *    The exact-solve kernel (algorithm 4) stores every solved row into all replicas through
+ *    NVLink peer pointers, i.e. the all-gather of the factor shards is fused into the producing
+ *    kernel; between half-sweeps only a device-side barrier over the same mappings remains.
  * ---------------------------------------------------------------------------------------- */
 
 /* Host-only: bounds[0..world] = first owner of each rank's range, from a CSR pointer array. */
 MRB_API int mrb_shard_ranges(const int* ptr, int owners, int world, int* bounds);
+/* Host-only: the owners rank receives under the dealt partition (degree-sorted owners dealt in
+ * snake order), in processing order; out has room for owners / world + 1 entries; returns the count. */
+MRB_API int mrb_dealt_owners(const int* ptr, int owners, int world, int rank, int* out);
 /* Restricts the problem to rank's row ranges and builds its work lists. */
 MRB_API int mrb_als_set_shard(mrb_als_problem* p, int rank, int world);
 /* out4 = {user_lo, user_hi, item_lo, item_hi}. */
@@ -179,6 +182,46 @@ MRB_API int mrb_als_open_peers(mrb_als_problem* p, const unsigned char* user_han
  * or on peers with access enabled); entry `rank` is ignored. */
 MRB_API int mrb_als_set_peer_pointers(mrb_als_problem* p, void* const* d_user_factor_replicas,
                                       void* const* d_item_factor_replicas, int world);
+/* ---- the peer group of the sharded product path (sharded.ShardedAls, exchange "p2p") --------
+ * Creation from a SLICE of the COO: the three pointers address ratings slice_begin ..
+ * slice_begin + slice_len - 1 of the num_ratings ratings of the problem; only they cross this
+ * rank's host link.  The index build is deferred: exchange the handles, mrb_als_open_peers_all,
+ * mrb_als_push_coo (own slice -> every peer over NVLink), mrb_als_peer_barrier, then
+ * mrb_als_build_index (id check, both groupings, this rank's work lists). */
+MRB_API int mrb_als_create_slice(const int* user_ids_slice, const int* item_ids_slice,
+                                 const double* ratings_slice, int slice_begin, int slice_len,
+                                 int num_ratings, int num_item_factors, int num_users,
+                                 int num_items, mrb_als_problem** out);
+/* 6 x 64 bytes: IPC handles of the user / item factor replicas, the three COO arrays and this
+ * process's barrier words.  An exported block is never returned to the driver (it is recycled by
+ * the library's arena), so a mapping a peer has cached can never dangle. */
+MRB_API int mrb_als_ipc_handles_all(mrb_als_problem* p, unsigned char* handles384);
+/* handles_by_rank: world x 384 bytes.  partition 1 deals the degree-sorted rows over the ranks
+ * in snake order (the product: rows are stored individually, ownership need not be contiguous);
+ * 0 cuts contiguous cost-balanced ranges. */
+MRB_API int mrb_als_open_peers_all(mrb_als_problem* p, const unsigned char* handles_by_rank,
+                                   int world, int rank, int partition);
+MRB_API int mrb_als_push_coo(mrb_als_problem* p);
+MRB_API int mrb_als_build_index(mrb_als_problem* p);
+/* Device-side barrier over the group (st.release.sys / ld.acquire.sys on the mapped barrier
+ * words), enqueued on `stream` (on_problem_stream == 0) or on the problem's own compute stream;
+ * it first joins everything the problem has put on its own streams.  Every rank must enqueue the
+ * same sequence of barriers.  A rank that never arrives trips a 10 s timeout, reported by
+ * mrb_peer_barrier_timed_out() (1 = timed out) and by mrb_als_download_factor_rows. */
+MRB_API int mrb_als_peer_barrier(mrb_als_problem* p, void* stream, int on_problem_stream);
+MRB_API int mrb_peer_barrier_timed_out(void);
+/* Rows [u_lo, u_hi) / [i_lo, i_hi) of FULL-size host factor arrays into the own replica and on
+ * into every peer replica (asynchronous, the arrays must stay valid until the next download);
+ * and the same rows back to the host (synchronises `stream`). */
+MRB_API int mrb_als_upload_factor_rows(mrb_als_problem* p, const double* user_factors,
+                                       const double* item_factors, int u_lo, int u_hi, int i_lo,
+                                       int i_hi);
+MRB_API int mrb_als_download_factor_rows(mrb_als_problem* p, double* user_factors,
+                                         double* item_factors, int u_lo, int u_hi, int i_lo,
+                                         int i_hi, void* stream);
+/* mrb_als_set_shard with the partition made explicit. */
+MRB_API int mrb_als_set_shard_partition(mrb_als_problem* p, int rank, int world, int partition);
+
 /* One exact half-sweep (user_side != 0: users) over this rank's rows, enqueued on `stream`
  * (a cudaStream_t); does not synchronise. */
 MRB_API int mrb_als_half_sweep(mrb_als_problem* p, int user_side, void* stream);

@@ -95,6 +95,8 @@ def _declare(dll):
     _B = ctypes.POINTER(ctypes.c_ubyte)
     dll.mrb_shard_ranges.restype = c_int
     dll.mrb_shard_ranges.argtypes = [_I, c_int, c_int, _I]
+    dll.mrb_dealt_owners.restype = c_int
+    dll.mrb_dealt_owners.argtypes = [_I, c_int, c_int, c_int, _I]
     dll.mrb_als_set_shard.restype = c_int
     dll.mrb_als_set_shard.argtypes = [c_void_p, c_int, c_int]
     dll.mrb_als_get_shard_ranges.restype = c_int
@@ -108,6 +110,27 @@ def _declare(dll):
     dll.mrb_als_set_peer_pointers.restype = c_int
     dll.mrb_als_set_peer_pointers.argtypes = [c_void_p, ctypes.POINTER(c_void_p),
                                               ctypes.POINTER(c_void_p), c_int]
+    dll.mrb_als_ipc_handles_all.restype = c_int
+    dll.mrb_als_ipc_handles_all.argtypes = [c_void_p, _B]
+    dll.mrb_als_open_peers_all.restype = c_int
+    dll.mrb_als_open_peers_all.argtypes = [c_void_p, _B, c_int, c_int, c_int]
+    dll.mrb_als_push_coo.restype = c_int
+    dll.mrb_als_push_coo.argtypes = [c_void_p]
+    dll.mrb_als_build_index.restype = c_int
+    dll.mrb_als_build_index.argtypes = [c_void_p]
+    dll.mrb_als_peer_barrier.restype = c_int
+    dll.mrb_als_peer_barrier.argtypes = [c_void_p, c_void_p, c_int]
+    dll.mrb_peer_barrier_timed_out.restype = c_int
+    dll.mrb_peer_barrier_timed_out.argtypes = []
+    dll.mrb_als_upload_factor_rows.restype = c_int
+    dll.mrb_als_upload_factor_rows.argtypes = [c_void_p, _D, _D, c_int, c_int, c_int, c_int]
+    dll.mrb_als_download_factor_rows.restype = c_int
+    dll.mrb_als_download_factor_rows.argtypes = [c_void_p, _D, _D, c_int, c_int, c_int, c_int, c_void_p]
+    dll.mrb_als_create_slice.restype = c_int
+    dll.mrb_als_create_slice.argtypes = [_I, _I, _D, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         ctypes.POINTER(c_void_p)]
+    dll.mrb_als_set_shard_partition.restype = c_int
+    dll.mrb_als_set_shard_partition.argtypes = [c_void_p, c_int, c_int, c_int]
     dll.mrb_als_half_sweep.restype = c_int
     dll.mrb_als_half_sweep.argtypes = [c_void_p, c_int, c_void_p]
     dll.mrb_als_shard_sse.restype = c_int

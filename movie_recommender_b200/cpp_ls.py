@@ -156,16 +156,28 @@ class AlsProblem:
     a benchmark can time sweeps with no host traffic in the timed region.
     """
 
-    def __init__(self, user_ids, item_ids, ratings, num_item_factors, num_users, num_items):
+    def __init__(self, user_ids, item_ids, ratings, num_item_factors, num_users, num_items,
+                 coo_slice=None):
+        """``coo_slice=(begin, end)``: multi-GPU creation -- this process uploads only ratings
+        begin..end-1 of the (full-length) arrays; the index build is deferred until the peers
+        have pushed theirs (``open_peer_group``, ``push_coo``, ``peer_barrier``,
+        ``build_index``; ``sharded.ShardedAls`` drives that sequence)."""
         self._user_ids = numpy.ascontiguousarray(user_ids, dtype=numpy.int32)
         self._item_ids = numpy.ascontiguousarray(item_ids, dtype=numpy.int32)
         self._ratings = numpy.ascontiguousarray(ratings, dtype=numpy.double)
         self.k, self.num_users, self.num_items = num_item_factors, num_users, num_items
         self._h = ctypes.c_void_p()
-        _lib.check(_dll.mrb_als_create(
-            _lib.ip(self._user_ids), _lib.ip(self._item_ids), len(self._ratings),
-            _lib.dp(self._ratings), num_item_factors, num_users, num_items,
-            ctypes.byref(self._h)))
+        if coo_slice is None:
+            _lib.check(_dll.mrb_als_create(
+                _lib.ip(self._user_ids), _lib.ip(self._item_ids), len(self._ratings),
+                _lib.dp(self._ratings), num_item_factors, num_users, num_items,
+                ctypes.byref(self._h)))
+        else:
+            b, e = int(coo_slice[0]), int(coo_slice[1])
+            _lib.check(_dll.mrb_als_create_slice(
+                _lib.ip(self._user_ids[b:e]), _lib.ip(self._item_ids[b:e]),
+                _lib.dp(self._ratings[b:e]), b, e - b, len(self._ratings), num_item_factors,
+                num_users, num_items, ctypes.byref(self._h)))
 
     def close(self):
         if self._h:
@@ -243,6 +255,11 @@ class AlsProblem:
         _lib.check(_dll.mrb_als_get_shard_ranges(self._h, _lib.ip(out)))
         return tuple(int(v) for v in out)   # user_lo, user_hi, item_lo, item_hi
 
+    def shard_ranges(self):
+        out = numpy.zeros(4, dtype=numpy.int32)
+        _lib.check(_dll.mrb_als_get_shard_ranges(self._h, _lib.ip(out)))
+        return tuple(int(v) for v in out)   # user_lo, user_hi, item_lo, item_hi
+
     def device_factors(self):
         """Raw device pointers (user_factors, item_factors)."""
         u, i = ctypes.c_void_p(), ctypes.c_void_p()
@@ -267,6 +284,47 @@ class AlsProblem:
         ai = (ctypes.c_void_p * world)(*item_ptrs)
         _lib.check(_dll.mrb_als_set_peer_pointers(self._h, au, ai, world))
 
+    # ---- the peer group of the sharded path: factor replicas, COO replicas, barrier words
+    def ipc_handles_all(self):
+        h = (ctypes.c_ubyte * 384)()
+        _lib.check(_dll.mrb_als_ipc_handles_all(self._h, h))
+        return bytes(h)
+
+    def open_peer_group(self, handles_by_rank, rank, partition=1):
+        """Maps every peer's buffers (``handles_by_rank[r]`` = rank r's ``ipc_handles_all()``)
+        and fixes this rank's place in the group; ``partition`` 1 deals the degree-sorted rows
+        over the ranks, 0 cuts contiguous cost-balanced ranges."""
+        world = len(handles_by_rank)
+        buf = (ctypes.c_ubyte * (384 * world)).from_buffer_copy(b"".join(handles_by_rank))
+        _lib.check(_dll.mrb_als_open_peers_all(self._h, buf, world, rank, partition))
+
+    def push_coo(self):
+        _lib.check(_dll.mrb_als_push_coo(self._h))
+
+    def build_index(self):
+        _lib.check(_dll.mrb_als_build_index(self._h))
+
+    def peer_barrier(self, stream=None):
+        """Device-side barrier over the peer group, enqueued on ``stream`` (a raw cudaStream_t)
+        or, with ``stream=None``, on the problem's own compute stream."""
+        _lib.check(_dll.mrb_als_peer_barrier(self._h, ctypes.c_void_p(stream or 0),
+                                             1 if stream is None else 0))
+
+    def upload_factor_rows(self, user_factors, item_factors, u_lo, u_hi, i_lo, i_hi):
+        """Rows of FULL-size host arrays into every replica (own upload + NVLink pushes),
+        asynchronous: the arrays are kept referenced until the next download / get_factors."""
+        self._pending_factors = (user_factors, item_factors)
+        _lib.check(_dll.mrb_als_upload_factor_rows(self._h, _lib.dp(user_factors), _lib.dp(item_factors),
+                                                   u_lo, u_hi, i_lo, i_hi))
+
+    def download_factor_rows(self, user_factors, item_factors, u_lo, u_hi, i_lo, i_hi, stream):
+        _lib.check(_dll.mrb_als_download_factor_rows(self._h, _lib.dp(user_factors), _lib.dp(item_factors),
+                                                     u_lo, u_hi, i_lo, i_hi, ctypes.c_void_p(stream)))
+        self._pending_factors = None
+
+    def set_shard_partition(self, rank, world, partition):
+        _lib.check(_dll.mrb_als_set_shard_partition(self._h, rank, world, partition))
+
     def half_sweep(self, user_side, stream):
         _lib.check(_dll.mrb_als_half_sweep(self._h, 1 if user_side else 0, ctypes.c_void_p(stream)))
 
@@ -288,6 +346,16 @@ def shard_ranges(ptr, world):
     bounds = numpy.zeros(world + 1, dtype=numpy.int32)
     _lib.check(_dll.mrb_shard_ranges(_lib.ip(ptr), len(ptr) - 1, world, _lib.ip(bounds)))
     return bounds
+
+
+def dealt_owners(ptr, rank, world):
+    """Host only: the rows rank owns under the dealt partition (degree-sorted rows dealt over the
+    ranks in snake order), in processing order."""
+    ptr = numpy.ascontiguousarray(ptr, dtype=numpy.int32)
+    owners = len(ptr) - 1
+    out = numpy.zeros(owners // world + 1, dtype=numpy.int32)
+    m = _lib.check(_dll.mrb_dealt_owners(_lib.ip(ptr), owners, world, rank, _lib.ip(out)))
+    return out[:m]
 
 
 def kernel_launches():

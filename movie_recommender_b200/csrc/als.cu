@@ -6,6 +6,18 @@
 namespace mrb {
 
 namespace {
+struct EventPair {   // RAII: released when an exception unwinds between record and read
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    EventPair() {
+        MRB_CUDA(cudaEventCreate(&e0));
+        MRB_CUDA(cudaEventCreate(&e1));
+    }
+    ~EventPair() {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+};
+
 // b[r] = ratings[r] - user_factors[(user_r + 1)*(k+1) - 1]      (matrix.cpp:1012-1031)
 __global__ void k_ratings_minus_bias(const double* __restrict__ ratings,
                                      const int* __restrict__ user_ids,
@@ -24,9 +36,20 @@ __global__ void k_check_ids(const int* __restrict__ ids, int n, int limit, int* 
 }  // namespace
 
 AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const double* ratings,
-                       int k, int num_users, int num_items)
-    : nnz_(nnz), k_(k), nu_(num_users), ni_(num_items) {
+                       int k, int num_users, int num_items, int slice_begin, int slice_len)
+    : nnz_(nnz), k_(k), nu_(num_users), ni_(num_items), slice_begin_(slice_begin),
+      slice_len_(slice_len) {
     MRB_REQUIRE(nnz >= 0 && k >= 1 && num_users >= 0 && num_items >= 0, "als: bad sizes");
+    const bool whole = slice_len < 0;
+    if (whole) { slice_begin_ = 0; slice_len_ = nnz; }
+    MRB_REQUIRE(slice_begin_ >= 0 && slice_len_ >= 0 && slice_begin_ + slice_len_ <= nnz,
+                "als: COO slice outside the ratings");
+    // RAII for the raw handles: a throwing constructor does not run the destructor
+    struct Cleanup {
+        AlsProblem* p;
+        bool armed = true;
+        ~Cleanup() { if (armed) p->destroy_handles(); }
+    } cleanup{this};
     MRB_CUDA(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
     MRB_CUDA(cudaStreamCreateWithFlags(&s_copy_, cudaStreamNonBlocking));
     MRB_CUDA(cudaEventCreateWithFlags(&ev_ratings_, cudaEventDisableTiming));
@@ -47,12 +70,50 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
     itf_.alloc(static_cast<size_t>(ni_) * k);
     // The ids go first on the compute stream; the ratings (half of the bytes, not needed by
     // the grouping) follow on the copy stream while the ids are being checked and grouped.
-    user_ids_.upload(user_ids, nnz, s_);
-    item_ids_.upload(item_ids, nnz, s_);
-    ratings_.upload(ratings, nnz, s_copy_);
+    if (slice_len_ > 0) {
+        MRB_CUDA(cudaMemcpyAsync(user_ids_.p + slice_begin_, user_ids, sizeof(int) * slice_len_,
+                                 cudaMemcpyHostToDevice, s_));
+        MRB_CUDA(cudaMemcpyAsync(item_ids_.p + slice_begin_, item_ids, sizeof(int) * slice_len_,
+                                 cudaMemcpyHostToDevice, s_));
+        MRB_CUDA(cudaMemcpyAsync(ratings_.p + slice_begin_, ratings, sizeof(double) * slice_len_,
+                                 cudaMemcpyHostToDevice, s_copy_));
+    }
     MRB_CUDA(cudaEventRecord(ev_ratings_, s_copy_));
     ratings_pending_ = true;
+    if (whole) build_index();
+    cleanup.armed = false;
+}
 
+void AlsProblem::set_coo_peers(const std::vector<int*>& user_ids, const std::vector<int*>& item_ids,
+                               const std::vector<double*>& ratings) {
+    uid_peers_ = user_ids;
+    iid_peers_ = item_ids;
+    rating_peers_ = ratings;
+}
+
+// The own slice into every peer's copy of the COO: ids behind their upload on the compute
+// stream, ratings behind theirs on the copy stream (device-to-peer copies run on the copy
+// engines over NVLink).  The caller follows up with a peer barrier on the compute stream.
+void AlsProblem::push_coo_slice() {
+    if (slice_len_ > 0) {
+        for (size_t r = 0; r < uid_peers_.size(); r++) {
+            if (static_cast<int>(r) == rank_ || uid_peers_[r] == nullptr) continue;
+            MRB_CUDA(cudaMemcpyAsync(uid_peers_[r] + slice_begin_, user_ids_.p + slice_begin_,
+                                     sizeof(int) * slice_len_, cudaMemcpyDefault, s_));
+            MRB_CUDA(cudaMemcpyAsync(iid_peers_[r] + slice_begin_, item_ids_.p + slice_begin_,
+                                     sizeof(int) * slice_len_, cudaMemcpyDefault, s_));
+            MRB_CUDA(cudaMemcpyAsync(rating_peers_[r] + slice_begin_, ratings_.p + slice_begin_,
+                                     sizeof(double) * slice_len_, cudaMemcpyDefault, s_copy_));
+        }
+    }
+    MRB_CUDA(cudaEventRecord(ev_ratings_, s_copy_));
+    // the barrier that follows on s_ must cover the rating pushes as well
+    MRB_CUDA(cudaStreamWaitEvent(s_, ev_ratings_, 0));
+}
+
+void AlsProblem::build_index() {
+    if (index_built_) return;
+    const int nnz = nnz_;
     // ids must be zero based and inside the factor arrays (python/full_data/cpp_ls.py:120-123);
     // the reference would read out of bounds, we refuse.
     DevBuf<int> bad(1);
@@ -70,29 +131,65 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
     }
 
     PhaseTimer t_idx("  index build (2 group_by)");
-    cudaEvent_t e0, e1;
-    MRB_CUDA(cudaEventCreate(&e0));
-    MRB_CUDA(cudaEventCreate(&e1));
-    MRB_CUDA(cudaEventRecord(e0, s_));
+    EventPair ev;
+    MRB_CUDA(cudaEventRecord(ev.e0, s_));
     stable_group_by(user_ids_.p, nnz, nu_, u_ptr_.p, u_idx_.p, s_);
     stable_group_by(item_ids_.p, nnz, ni_, i_ptr_.p, i_idx_.p, s_);
-    MRB_CUDA(cudaEventRecord(e1, s_));
-    MRB_CUDA(cudaEventSynchronize(e1));
-    MRB_CUDA(cudaEventElapsedTime(&index_ms_, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    MRB_CUDA(cudaEventRecord(ev.e1, s_));
+    MRB_CUDA(cudaEventSynchronize(ev.e1));
+    MRB_CUDA(cudaEventElapsedTime(&index_ms_, ev.e0, ev.e1));
+    index_built_ = true;
+}
+
+void AlsProblem::destroy_handles() {
+    for (cudaEvent_t e : gram_events_) cudaEventDestroy(e);
+    gram_events_.clear();
+    for (cudaEvent_t* e : {&ev_ratings_, &ev_factors_, &ev_user_done_, &ev_uf_copied_, &ev_prepared_}) {
+        if (*e) cudaEventDestroy(*e);
+        *e = nullptr;
+    }
+    if (s_copy_) cudaStreamDestroy(s_copy_);
+    if (s_) cudaStreamDestroy(s_);
+    s_copy_ = s_ = nullptr;
 }
 
 AlsProblem::~AlsProblem() {
     if (s_copy_) cudaStreamSynchronize(s_copy_);
     if (s_) cudaStreamSynchronize(s_);
-    for (cudaEvent_t e : gram_events_) cudaEventDestroy(e);
-    gram_events_.clear();
     gram_.reset();
-    for (cudaEvent_t e : {ev_ratings_, ev_factors_, ev_user_done_, ev_uf_copied_, ev_prepared_})
-        if (e) cudaEventDestroy(e);
-    if (s_copy_) cudaStreamDestroy(s_copy_);
-    if (s_) cudaStreamDestroy(s_);
+    destroy_handles();
+}
+
+// Rows of the factor matrices from full-size host arrays: into the own replica, then on into
+// every peer replica over NVLink (each byte crosses the host link once per box).  Asynchronous
+// on the copy stream; the compute stream picks the event up like after set_factors_async.
+void AlsProblem::upload_factor_rows(const double* user_factors, const double* item_factors,
+                                    int u_lo, int u_hi, int i_lo, int i_hi) {
+    MRB_REQUIRE(0 <= u_lo && u_lo <= u_hi && u_hi <= nu_ && 0 <= i_lo && i_lo <= i_hi && i_hi <= ni_,
+                "als: factor row range outside the matrices");
+    const size_t n = k_ + 1, uo = static_cast<size_t>(u_lo) * n, ub = static_cast<size_t>(u_hi - u_lo) * n;
+    const size_t io = static_cast<size_t>(i_lo) * k_, ib = static_cast<size_t>(i_hi - i_lo) * k_;
+    if (ib) MRB_CUDA(cudaMemcpyAsync(itf_.p + io, item_factors + io, sizeof(double) * ib, cudaMemcpyHostToDevice, s_copy_));
+    if (ub) MRB_CUDA(cudaMemcpyAsync(uf_.p + uo, user_factors + uo, sizeof(double) * ub, cudaMemcpyHostToDevice, s_copy_));
+    for (size_t r = 0; r < uf_peers_.size(); r++) {
+        if (static_cast<int>(r) == rank_ || uf_peers_[r] == nullptr) continue;
+        if (ib) MRB_CUDA(cudaMemcpyAsync(itf_peers_[r] + io, itf_.p + io, sizeof(double) * ib, cudaMemcpyDefault, s_copy_));
+        if (ub) MRB_CUDA(cudaMemcpyAsync(uf_peers_[r] + uo, uf_.p + uo, sizeof(double) * ub, cudaMemcpyDefault, s_copy_));
+    }
+    MRB_CUDA(cudaEventRecord(ev_factors_, s_copy_));
+    factors_pending_ = true;
+    factors_recorded_ = true;
+}
+
+void AlsProblem::download_factor_rows(double* user_factors, double* item_factors, int u_lo,
+                                      int u_hi, int i_lo, int i_hi, cudaStream_t after) {
+    MRB_REQUIRE(0 <= u_lo && u_lo <= u_hi && u_hi <= nu_ && 0 <= i_lo && i_lo <= i_hi && i_hi <= ni_,
+                "als: factor row range outside the matrices");
+    const size_t n = k_ + 1, uo = static_cast<size_t>(u_lo) * n, ub = static_cast<size_t>(u_hi - u_lo) * n;
+    const size_t io = static_cast<size_t>(i_lo) * k_, ib = static_cast<size_t>(i_hi - i_lo) * k_;
+    if (ub) MRB_CUDA(cudaMemcpyAsync(user_factors + uo, uf_.p + uo, sizeof(double) * ub, cudaMemcpyDeviceToHost, after));
+    if (ib) MRB_CUDA(cudaMemcpyAsync(item_factors + io, itf_.p + io, sizeof(double) * ib, cudaMemcpyDeviceToHost, after));
+    MRB_CUDA(cudaStreamSynchronize(after));
 }
 
 void AlsProblem::wait_ratings() {
@@ -149,9 +246,8 @@ void AlsProblem::get_factors(double* user_factors, double* item_factors) {
 
 AlsRunInfo AlsProblem::run(int algorithm, double min_r_decrease, int max_iteration,
                            int thread_count) {
-    cudaEvent_t e0, e1;
-    MRB_CUDA(cudaEventCreate(&e0));
-    MRB_CUDA(cudaEventCreate(&e1));
+    EventPair ev;
+    cudaEvent_t e0 = ev.e0, e1 = ev.e1;
     MRB_CUDA(cudaEventRecord(e0, s_));
     const long long launches0 = g_kernel_launches.load();
     AlsRunInfo info;
@@ -163,8 +259,6 @@ AlsRunInfo AlsProblem::run(int algorithm, double min_r_decrease, int max_iterati
     MRB_CUDA(cudaEventSynchronize(e1));
     MRB_CUDA(cudaEventElapsedTime(&info.device_ms, e0, e1));
     info.kernel_launches = static_cast<int>(g_kernel_launches.load() - launches0);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return info;
 }
 

@@ -34,13 +34,35 @@ struct AlsRunInfo {
 
 // bounds[0..world]: nnz-balanced contiguous owner ranges from a CSR pointer array (host).
 void balanced_ranges(const int* ptr, int owners, int world, int* bounds);
+// Host mirror of the dealt partition: writes rank's owners (processing order), returns the count.
+int dealt_owners_host(const int* ptr, int owners, int world, int rank, int* out);
 
 class AlsProblem {
 public:
     // Host pointers; uploads and builds both groupings (K4).
+    // Multi-GPU creation from a SLICE of the COO (every byte crosses the host link once): the
+    // three host pointers address ratings slice_begin .. slice_begin + slice_len - 1 of the nnz
+    // ratings; they are uploaded into place, the index build is deferred until the peers have
+    // pushed their slices over NVLink (push_coo_slice on every rank, a peer barrier, then
+    // build_index).  slice_len < 0: the whole COO, index built at once (the one-GPU path).
     AlsProblem(const int* user_ids, const int* item_ids, int nnz, const double* ratings, int k,
-               int num_users, int num_items);
+               int num_users, int num_items, int slice_begin = 0, int slice_len = -1);
     ~AlsProblem();
+    void build_index();                      // id check + the two stable groupings
+    // peer replicas of the three COO arrays, index = rank (own entry ignored)
+    void set_coo_peers(const std::vector<int*>& user_ids, const std::vector<int*>& item_ids,
+                       const std::vector<double*>& ratings);
+    void push_coo_slice();                   // own slice -> every peer replica (copy engines)
+    int* d_user_ids() { return user_ids_.p; }
+    int* d_item_ids() { return item_ids_.p; }
+    double* d_ratings() { return ratings_.p; }
+    // rows [u_lo, u_hi) of the user factors and [i_lo, i_hi) of the item factors from FULL-size
+    // host arrays into the own replica and on into every peer replica (asynchronous); the
+    // counterpart copies the same rows back and synchronises.
+    void upload_factor_rows(const double* user_factors, const double* item_factors, int u_lo,
+                            int u_hi, int i_lo, int i_hi);
+    void download_factor_rows(double* user_factors, double* item_factors, int u_lo, int u_hi,
+                              int i_lo, int i_hi, cudaStream_t after);
 
     void set_factors(const double* user_factors, const double* item_factors);  // host -> device
     void get_factors(double* user_factors, double* item_factors);              // device -> host
@@ -62,7 +84,10 @@ public:
     // contiguous ranges over `world` ranks; every rank keeps full replicas of both factor
     // matrices.  The solve kernel stores each solved row into EVERY replica (peer pointers over
     // NVLink), so the all-gather of the factor shards is fused into the producing kernel.
-    void set_shard(int rank, int world);
+    // partition 0: contiguous ranges of equal cost (needed by an NCCL range exchange);
+    // partition 1: the degree-sorted owner list dealt over the ranks in snake order (rows are
+    // stored individually into every replica, so ownership need not be contiguous)
+    void set_shard(int rank, int world, int partition = 0);
     void shard_ranges(int* user_lo, int* user_hi, int* item_lo, int* item_hi) const;
     // peer replicas of the factor matrices, index = rank (entry `rank` may be the local buffer)
     void set_peers(const std::vector<double*>& user_factor_peers,
@@ -70,6 +95,10 @@ public:
     // One exact (algorithm 4) half-sweep over this rank's rows, enqueued on `stream`.
     void half_sweep(bool user_side, cudaStream_t stream);
     void half_sweep_prepare() { ensure_gram(); }   // builds this rank's work lists
+    // A caller-provided stream (half_sweep, shard_sse, a peer barrier) waits for everything this
+    // object has put on its own streams: the uploads, the pushes to the peers and the grouped
+    // copies made by ensure_gram.
+    void order_after_inputs(cudaStream_t stream);
     // Sum of this rank's per-row residuals of the last item half-sweep (after a sync).
     double shard_sse(cudaStream_t stream);
     float collect_gram_ms();   // CUDA-event time of the half_sweep launches since the last call
@@ -93,10 +122,8 @@ private:
     void ensure_gram();
     void wait_ratings();   // s_ waits for the ratings upload (second stream)
     void wait_factors();   // s_ waits for a pending set_factors_async
-    // A caller-provided stream (half_sweep, shard_sse) waits for everything this object has put
-    // on its own streams: the uploads and the grouped copies made by ensure_gram.
-    void order_after_inputs(cudaStream_t stream);
     void launch_half(bool user_side, cudaStream_t stream, int epilogue);
+    void destroy_handles();
 
     int nnz_, k_, nu_, ni_;
     cudaStream_t s_ = nullptr, s_copy_ = nullptr;
@@ -109,7 +136,11 @@ private:
     DevBuf<int> user_ids_, item_ids_, u_ptr_, u_idx_, i_ptr_, i_idx_;
     DevBuf<double> ratings_, uf_, itf_, rmb_;
     float index_ms_ = 0;
-    int rank_ = 0, world_ = 1;
+    int rank_ = 0, world_ = 1, partition_ = 0;
+    int slice_begin_ = 0, slice_len_ = -1;
+    bool index_built_ = false;
+    std::vector<int*> uid_peers_, iid_peers_;
+    std::vector<double*> rating_peers_;
     std::vector<double*> uf_peers_, itf_peers_;
     std::vector<cudaEvent_t> gram_events_;
 public:

@@ -25,6 +25,7 @@
 // Gram matrices are summed in SEGMENT ORDER by whichever warp finishes last, so the result does
 // not depend on scheduling (deterministic, no floating-point atomics).
 #include <algorithm>
+#include <atomic>
 #include <numeric>
 #include <vector>
 
@@ -561,6 +562,25 @@ void balanced_ranges(const int* ptr, int owners, int world, int* bounds) {
     bounds[world] = owners;
 }
 
+// Host mirror of the dealt partition (k_lpt_keys + stable_group_by + k_deal_order): the owners
+// rank r receives, in its processing order.  Used by the CPU tests of the N > 1 host logic.
+int dealt_owners_host(const int* ptr, int owners, int world, int rank, int* out) {
+    std::vector<int> order(static_cast<size_t>(owners));
+    std::iota(order.begin(), order.end(), 0);
+    auto key = [&](int o) {
+        const int deg = ptr[o + 1] - ptr[o];
+        return deg >= 65535 ? 0 : 65535 - deg;
+    };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
+    const int full = owners / world, rest = owners % world;
+    const int m = full + (rank < rest ? 1 : 0);
+    for (int t = 0; t < m; t++) {
+        const int off = (t < full && (t & 1)) ? world - 1 - rank : rank;
+        out[t] = order[static_cast<size_t>(t) * world + off];
+    }
+    return m;
+}
+
 namespace {
 
 struct Side {
@@ -650,12 +670,37 @@ __global__ void k_write_work(const int* __restrict__ ptr, int lo, int m,
 // while the ratings are still on their way to the device.  Host round trips: the pointer array
 // when the rows are sharded (the balanced ranges are a host decision every rank must agree on),
 // and four totals.
+// rank's share of the degree-sorted owner list, dealt in snake order: block t of `world`
+// consecutive owners gives position rank (t even) or world-1-rank (t odd) to this rank, so the
+// per-rank sums of (ratings + solve cost) differ by less than one heavy row
+__global__ void k_deal_order(const int* __restrict__ order, int owners, int rank, int world,
+                             int m_r, int* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m_r) return;
+    // an incomplete last block (t == owners / world) is dealt in plain order to the first ranks
+    const int off = (t < owners / world && (t & 1)) ? world - 1 - rank : rank;
+    out[t] = order[t * world + off];
+}
+
+// number of owners rank r receives
+int dealt_count(int owners, int rank, int world) {
+    const int full = owners / world, rest = owners % world;
+    if (rest == 0) return full;
+    // incomplete last block t = full: dealt in PLAIN order to ranks 0 .. rest-1
+    return full + (rank < rest ? 1 : 0);
+}
+
+// This rank's owners and its work lists.  Needs the CSR pointers only, so it is enqueued
+// while the ratings are still on their way to the device.  Host round trips: the pointer array
+// when the rows are sharded in contiguous ranges (the balanced ranges are a host decision every
+// rank must agree on), and four totals.
 void build_side_lists(Side& sd, const int* d_ptr, int owners, int nnz, int rank, int world,
-                      cudaStream_t s) {
+                      int partition, cudaStream_t s) {
     PhaseTimer t2("  side: work lists");
     sd.lo = 0;
     sd.hi = owners;
-    if (world > 1) {
+    const bool dealt = world > 1 && partition == 1;
+    if (world > 1 && !dealt) {
         std::vector<int> ptr(static_cast<size_t>(owners) + 1);
         MRB_CUDA(cudaMemcpyAsync(ptr.data(), d_ptr, sizeof(int) * ptr.size(), cudaMemcpyDeviceToHost, s));
         MRB_CUDA(cudaStreamSynchronize(s));
@@ -664,29 +709,37 @@ void build_side_lists(Side& sd, const int* d_ptr, int owners, int nnz, int rank,
         sd.lo = bounds[rank];
         sd.hi = bounds[rank + 1];
     }
-    const int m = sd.hi - sd.lo;
+    const int m_all = sd.hi - sd.lo;                       // owners that are sorted by degree
+    const int m = dealt ? dealt_count(owners, rank, world) : m_all;   // owners of this rank
     sd.n_work = sd.n_multi = sd.n_slots = sd.n_owner_items = 0;
     sd.owner_order.alloc(static_cast<size_t>(std::max(m, 1)));
     // every owner has at most deg / GRAM_SEG + 1 items
     sd.work.alloc(static_cast<size_t>(m) + static_cast<size_t>(nnz) / GRAM_SEG + 1);
     if (m == 0) return;
-    DevBuf<int> key(m), kptr(LPT_KEYS + 1), order(m);
+    DevBuf<int> key(m_all), kptr(LPT_KEYS + 1), order(m_all), mine;
     DevBuf<int> counts(4 * (static_cast<size_t>(m) + 1));
     int* item_at = counts.p;
     int* multi_at = item_at + m + 1;
     int* slot_at = multi_at + m + 1;
     int* nonempty_at = slot_at + m + 1;
-    k_lpt_keys<<<ceil_div(m, 256), 256, 0, s>>>(d_ptr, sd.lo, m, key.p);
+    k_lpt_keys<<<ceil_div(m_all, 256), 256, 0, s>>>(d_ptr, sd.lo, m_all, key.p);
     MRB_LAUNCHED(1);
-    stable_group_by(key.p, m, LPT_KEYS, kptr.p, order.p, s);
-    k_owner_counts<<<ceil_div(m + 1, 256), 256, 0, s>>>(d_ptr, sd.lo, m, order.p, item_at, multi_at,
+    stable_group_by(key.p, m_all, LPT_KEYS, kptr.p, order.p, s);
+    const int* my_order = order.p;
+    if (dealt) {
+        mine.alloc(m);
+        k_deal_order<<<ceil_div(m, 256), 256, 0, s>>>(order.p, owners, rank, world, m, mine.p);
+        MRB_LAUNCHED(1);
+        my_order = mine.p;
+    }
+    k_owner_counts<<<ceil_div(m + 1, 256), 256, 0, s>>>(d_ptr, sd.lo, m, my_order, item_at, multi_at,
                                                        slot_at, nonempty_at);
     MRB_LAUNCHED(1);
     exclusive_scan_i32(item_at, item_at, m + 1, s);
     exclusive_scan_i32(multi_at, multi_at, m + 1, s);
     exclusive_scan_i32(slot_at, slot_at, m + 1, s);
     exclusive_scan_i32(nonempty_at, nonempty_at, m + 1, s);
-    k_write_work<<<ceil_div(m, 256), 256, 0, s>>>(d_ptr, sd.lo, m, order.p, item_at, multi_at,
+    k_write_work<<<ceil_div(m, 256), 256, 0, s>>>(d_ptr, sd.lo, m, my_order, item_at, multi_at,
                                                  slot_at, nonempty_at, sd.work.p, sd.owner_order.p);
     MRB_LAUNCHED(1);
     MRB_CUDA(cudaGetLastError());
@@ -704,9 +757,14 @@ void build_side_lists(Side& sd, const int* d_ptr, int owners, int nnz, int rank,
 template <int M8, bool USER, int EPI>
 void launch_gram(const GramArgs& a, int sms, cudaStream_t s) {
     auto kern = k_gram<M8, USER, EPI>;
-    static int per_sm = 0;
-    if (per_sm == 0)
+    // one process drives one GPU model; the value is idempotent, so a benign race is excluded by
+    // making the cache atomic
+    static std::atomic<int> cached{0};
+    int per_sm = cached.load(std::memory_order_relaxed);
+    if (per_sm == 0) {
         MRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GRAM_WARPS * 32, 0));
+        cached.store(per_sm, std::memory_order_relaxed);
+    }
     MRB_REQUIRE(per_sm >= 1, "gram kernel does not fit on an SM");
     // persistent CTAs: one wave that fills every SM, work items handed out dynamically
     const int grid = std::min(sms * per_sm, ceil_div(a.n_work, GRAM_WARPS));
@@ -792,7 +850,8 @@ struct AlsProblem::GramState {
     DevBuf<double> sse_owner;  // per-item residual sum of squares from the factorisation
     int sms = 148;
     int st_doubles = 0;
-    int built_rank = -1, built_world = -1;
+    int built_rank = -1, built_world = -1, built_partition = -1;
+    int per_sm_block_u = 0, per_sm_block_i = 0;   // occupancy of k_gram_block on this device
     // wide ranks (k > 54): per-batch stored matrices of the block-Gram + shared-memory Cholesky path
     bool wide = false;
     DevBuf<double> wG, wg, wcorner;
@@ -806,15 +865,17 @@ void AlsProblem::ensure_gram() {
     const int n_u = k_ + 1;
     const int m8 = (n_u + 1 + 7) / 8;
     MRB_REQUIRE(n_u <= 160, "als algorithm 3/4: rank above 159 is not supported");
-    if (gram_ && gram_->built_rank == rank_ && gram_->built_world == world_) return;
+    if (gram_ && gram_->built_rank == rank_ && gram_->built_world == world_ &&
+        gram_->built_partition == partition_) return;
+    build_index();
     PhaseTimer t_g("ensure_gram (work lists)");
     gram_ = std::make_shared<GramState>();
     GramState& g = *gram_;
     int dev = 0;
     MRB_CUDA(cudaGetDevice(&dev));
     MRB_CUDA(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, dev));
-    build_side_lists(g.user, u_ptr_.p, nu_, nnz_, rank_, world_, s_);
-    build_side_lists(g.item, i_ptr_.p, ni_, nnz_, rank_, world_, s_);
+    build_side_lists(g.user, u_ptr_.p, nu_, nnz_, rank_, world_, partition_, s_);
+    build_side_lists(g.item, i_ptr_.p, ni_, nnz_, rank_, world_, partition_, s_);
     wait_ratings();
     build_side_gather(g.user, u_idx_.p, item_ids_.p, ratings_.p, nnz_, s_);
     build_side_gather(g.item, i_idx_.p, user_ids_.p, ratings_.p, nnz_, s_);
@@ -837,6 +898,7 @@ void AlsProblem::ensure_gram() {
     g.sse_owner.alloc(static_cast<size_t>(std::max(ni_, 1)));
     g.built_rank = rank_;
     g.built_world = world_;
+    g.built_partition = partition_;
 }
 
 // One k_gram launch (algorithm 4) over this rank's rows of one side, timed by a pair of events.
@@ -878,8 +940,7 @@ void AlsProblem::launch_half(bool user_side, cudaStream_t stream, int epilogue) 
             c.sse_out = g.sse_owner.p;
         }
         if (sd.n_owner_items == 0) return;
-        static int per_sm_u = 0, per_sm_i = 0;
-        int& per_sm = user_side ? per_sm_u : per_sm_i;
+        int& per_sm = user_side ? g.per_sm_block_u : g.per_sm_block_i;
         if (per_sm == 0) {
             if (user_side) MRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gram_block<true>, GRAM_WARPS * 32, 0));
             else MRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gram_block<false>, GRAM_WARPS * 32, 0));
@@ -888,9 +949,11 @@ void AlsProblem::launch_half(bool user_side, cudaStream_t stream, int epilogue) 
         const size_t chol_smem = sizeof(double) * (static_cast<size_t>(n + 1) * LD + 3 * n);
         MRB_CUDA(cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(chol_smem)));
-        cudaEvent_t e0, e1;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
         MRB_CUDA(cudaEventCreate(&e0));
+        gram_events_.push_back(e0);          // owned by the list from here on (no leak on throw)
         MRB_CUDA(cudaEventCreate(&e1));
+        gram_events_.push_back(e1);
         MRB_CUDA(cudaEventRecord(e0, stream));
         const bool store = epilogue == EPI_STORE;
         if (store) {
@@ -927,8 +990,6 @@ void AlsProblem::launch_half(bool user_side, cudaStream_t stream, int epilogue) 
             }
         }
         MRB_CUDA(cudaEventRecord(e1, stream));
-        gram_events_.push_back(e0);
-        gram_events_.push_back(e1);
         return;
     }
     MRB_CUDA(cudaMemsetAsync(g.counters.p, 0, sizeof(int) * g.counters.n, stream));
@@ -961,9 +1022,11 @@ void AlsProblem::launch_half(bool user_side, cudaStream_t stream, int epilogue) 
         a.sse_out = g.sse_owner.p;
     }
     if (sd.n_work == 0) return;
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     MRB_CUDA(cudaEventCreate(&e0));
+    gram_events_.push_back(e0);
     MRB_CUDA(cudaEventCreate(&e1));
+    gram_events_.push_back(e1);
     MRB_CUDA(cudaEventRecord(e0, stream));
     if (epilogue == EPI_STORE) {
         // rows without ratings are not in the work list: their blocks must read as zero
@@ -979,17 +1042,18 @@ void AlsProblem::launch_half(bool user_side, cudaStream_t stream, int epilogue) 
         else dispatch_gram<false, EPI_SOLVE>(a, g.sms, stream);
     }
     MRB_CUDA(cudaEventRecord(e1, stream));
-    gram_events_.push_back(e0);
-    gram_events_.push_back(e1);
 }
 
 float AlsProblem::collect_gram_ms() {
     float total = 0;
     for (size_t i = 0; i + 1 < gram_events_.size(); i += 2) {
         float ms = 0;
-        MRB_CUDA(cudaEventSynchronize(gram_events_[i + 1]));
-        MRB_CUDA(cudaEventElapsedTime(&ms, gram_events_[i], gram_events_[i + 1]));
-        total += ms;
+        // a pair whose second event was never recorded (an exception in between) is skipped
+        if (cudaEventSynchronize(gram_events_[i + 1]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, gram_events_[i], gram_events_[i + 1]) == cudaSuccess)
+            total += ms;
+        else
+            cudaGetLastError();
         cudaEventDestroy(gram_events_[i]);
         cudaEventDestroy(gram_events_[i + 1]);
     }
@@ -997,10 +1061,12 @@ float AlsProblem::collect_gram_ms() {
     return total;
 }
 
-void AlsProblem::set_shard(int rank, int world) {
+void AlsProblem::set_shard(int rank, int world, int partition) {
     MRB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "als: bad shard (rank, world)");
+    MRB_REQUIRE(partition == 0 || partition == 1, "als: partition must be 0 (ranges) or 1 (dealt)");
     rank_ = rank;
     world_ = world;
+    partition_ = partition;
 }
 
 void AlsProblem::shard_ranges(int* user_lo, int* user_hi, int* item_lo, int* item_hi) const {

@@ -3,6 +3,7 @@
 #include <map>
 #include <mutex>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "common.cuh"
@@ -15,6 +16,9 @@ struct Arena {
     // (device, rounded size) -> free blocks
     std::map<std::pair<int, size_t>, std::vector<void*>> free_lists;
     std::unordered_map<void*, std::pair<int, size_t>> live;   // block -> (device, rounded size)
+    // blocks whose CUDA IPC handle went to another process: a peer may hold a cached mapping, so
+    // they are recycled through the free lists for the life of the process and never cudaFree'd
+    std::unordered_set<void*> exported;
     bool enabled = std::getenv("MRB_NO_CACHE") == nullptr;
 };
 Arena& arena() {
@@ -32,9 +36,20 @@ size_t round_size(size_t bytes) {
 void arena_trim() {
     Arena& a = arena();
     std::lock_guard<std::mutex> lock(a.mu);
-    for (auto& kv : a.free_lists)
-        for (void* p : kv.second) cudaFree(p);
-    a.free_lists.clear();
+    for (auto& kv : a.free_lists) {
+        std::vector<void*> keep;
+        for (void* p : kv.second) {
+            if (a.exported.count(p)) keep.push_back(p);
+            else cudaFree(p);
+        }
+        kv.second.swap(keep);
+    }
+}
+
+void arena_pin_exported(void* p) {
+    Arena& a = arena();
+    std::lock_guard<std::mutex> lock(a.mu);
+    a.exported.insert(p);
 }
 
 void* arena_alloc(size_t bytes) {
@@ -77,7 +92,7 @@ void arena_free(void* p) {
     if (it == a.live.end()) { cudaFree(p); return; }
     const auto key = it->second;
     a.live.erase(it);
-    if (a.enabled) a.free_lists[key].push_back(p);
+    if (a.enabled || a.exported.count(p)) a.free_lists[key].push_back(p);
     else cudaFree(p);
 }
 

@@ -17,6 +17,7 @@
 #include "similarity.cuh"
 #include "cosim.cuh"
 #include "prep.cuh"
+#include "peer.cuh"
 
 namespace mrb {
 static thread_local std::string g_last_error;
@@ -231,12 +232,12 @@ int mrb_csr_transpose(int rows, int cols, const int* rowptr, const int* colidx, 
 
 struct mrb_als_problem {
     AlsProblem impl;
-    // (peer mappings live in g_ipc_cache, not here: they outlive the problem)
-    mrb_als_problem(const int* u, const int* i, int nnz, const double* r, int k, int nu, int ni)
-        : impl(u, i, nnz, r, k, nu, ni) {}
-    ~mrb_als_problem() {
-
-    }
+    // (peer mappings live in the process-wide IPC cache, not here: they outlive the problem)
+    int* barrier_peers[PEER_MAX] = {nullptr};
+    int rank = 0, world = 1;
+    mrb_als_problem(const int* u, const int* i, int nnz, const double* r, int k, int nu, int ni,
+                    int slice_begin = 0, int slice_len = -1)
+        : impl(u, i, nnz, r, k, nu, ni, slice_begin, slice_len) {}
 };
 
 int mrb_als_create(const int* user_ids, const int* item_ids, int num_ratings,
@@ -331,9 +332,19 @@ int mrb_shard_ranges(const int* ptr, int owners, int world, int* bounds) {
     });
 }
 
+int mrb_dealt_owners(const int* ptr, int owners, int world, int rank, int* out) {
+    return guarded([&] {
+        MRB_REQUIRE(ptr != nullptr && out != nullptr && owners >= 0 && world >= 1 && rank >= 0 &&
+                    rank < world, "mrb_dealt_owners: bad arguments");
+        return dealt_owners_host(ptr, owners, world, rank, out);
+    });
+}
+
 int mrb_als_set_shard(mrb_als_problem* p, int rank, int world) {
     return guarded([&] {
         MRB_REQUIRE(p != nullptr, "null problem");
+        p->rank = rank;
+        p->world = world;
         p->impl.set_shard(rank, world);
         p->impl.half_sweep_prepare();
         return 0;
@@ -361,39 +372,10 @@ int mrb_als_ipc_handles(mrb_als_problem* p, unsigned char* user_handle64,
                         unsigned char* item_handle64) {
     return guarded([&] {
         MRB_REQUIRE(p != nullptr, "null problem");
-        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-        cudaIpcMemHandle_t hu, hi;
-        MRB_CUDA(cudaIpcGetMemHandle(&hu, p->impl.user_factors()));
-        MRB_CUDA(cudaIpcGetMemHandle(&hi, p->impl.item_factors()));
-        std::memcpy(user_handle64, &hu, 64);
-        std::memcpy(item_handle64, &hi, 64);
+        ipc_export(p->impl.user_factors(), user_handle64);
+        ipc_export(p->impl.item_factors(), item_handle64);
         return 0;
     });
-}
-
-// Peer mappings are cached by handle for the life of the process (closed by mrb_trim_memory):
-// the arena hands a re-created problem the same device blocks, so a training loop that builds
-// one problem per step opens every peer buffer once (cudaIpcOpenMemHandle costs milliseconds).
-static std::mutex g_ipc_mutex;
-static std::map<std::string, void*> g_ipc_cache;
-
-static void* ipc_open_cached(const unsigned char* handle64) {
-    std::lock_guard<std::mutex> lock(g_ipc_mutex);
-    const std::string key(reinterpret_cast<const char*>(handle64), 64);
-    auto it = g_ipc_cache.find(key);
-    if (it != g_ipc_cache.end()) return it->second;
-    cudaIpcMemHandle_t h;
-    std::memcpy(&h, handle64, 64);
-    void* q = nullptr;
-    MRB_CUDA(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
-    g_ipc_cache.emplace(key, q);
-    return q;
-}
-
-static void ipc_close_all() {
-    std::lock_guard<std::mutex> lock(g_ipc_mutex);
-    for (auto& kv : g_ipc_cache) cudaIpcCloseMemHandle(kv.second);
-    g_ipc_cache.clear();
 }
 
 int mrb_als_open_peers(mrb_als_problem* p, const unsigned char* user_handles,
@@ -412,6 +394,141 @@ int mrb_als_open_peers(mrb_als_problem* p, const unsigned char* user_handles,
             ip[r] = static_cast<double*>(ipc_open_cached(item_handles + 64 * r));
         }
         p->impl.set_peers(up, ip);
+        return 0;
+    });
+}
+
+// ---- the whole peer group of a sharded problem: factor replicas, COO replicas, barrier words
+int mrb_als_ipc_handles_all(mrb_als_problem* p, unsigned char* handles /* 6 x 64 bytes */) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr && handles != nullptr, "null argument");
+        ipc_export(p->impl.user_factors(), handles);
+        ipc_export(p->impl.item_factors(), handles + 64);
+        ipc_export(p->impl.d_user_ids(), handles + 128);
+        ipc_export(p->impl.d_item_ids(), handles + 192);
+        ipc_export(p->impl.d_ratings(), handles + 256);
+        cudaIpcMemHandle_t h;
+        MRB_CUDA(cudaIpcGetMemHandle(&h, peer_barrier_words()));
+        std::memcpy(handles + 320, &h, 64);
+        return 0;
+    });
+}
+
+int mrb_als_open_peers_all(mrb_als_problem* p, const unsigned char* handles_by_rank, int world,
+                           int rank, int partition) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr && world >= 1 && world <= PEER_MAX && rank >= 0 && rank < world,
+                    "mrb_als_open_peers_all: bad arguments");
+        std::vector<double*> up(world, nullptr), ip(world, nullptr), rp(world, nullptr);
+        std::vector<int*> uid(world, nullptr), iid(world, nullptr);
+        for (int r = 0; r < world; r++) {
+            const unsigned char* h = handles_by_rank + static_cast<size_t>(r) * 384;
+            if (r == rank) {
+                up[r] = p->impl.user_factors();
+                ip[r] = p->impl.item_factors();
+                uid[r] = p->impl.d_user_ids();
+                iid[r] = p->impl.d_item_ids();
+                rp[r] = p->impl.d_ratings();
+                p->barrier_peers[r] = peer_barrier_words();
+                continue;
+            }
+            up[r] = static_cast<double*>(ipc_open_cached(h));
+            ip[r] = static_cast<double*>(ipc_open_cached(h + 64));
+            uid[r] = static_cast<int*>(ipc_open_cached(h + 128));
+            iid[r] = static_cast<int*>(ipc_open_cached(h + 192));
+            rp[r] = static_cast<double*>(ipc_open_cached(h + 256));
+            p->barrier_peers[r] = static_cast<int*>(ipc_open_cached(h + 320));
+        }
+        p->rank = rank;
+        p->world = world;
+        p->impl.set_shard(rank, world, partition);   // rank known from here on (pushes skip it)
+        p->impl.set_peers(up, ip);
+        p->impl.set_coo_peers(uid, iid, rp);
+        return 0;
+    });
+}
+
+int mrb_als_push_coo(mrb_als_problem* p) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        p->impl.push_coo_slice();
+        return 0;
+    });
+}
+
+int mrb_als_build_index(mrb_als_problem* p) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        p->impl.build_index();
+        p->impl.half_sweep_prepare();   // this rank's work lists
+        return 0;
+    });
+}
+
+int mrb_als_peer_barrier(mrb_als_problem* p, void* stream, int on_problem_stream) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        if (p->world == 1) return 0;
+        MRB_REQUIRE(p->barrier_peers[p->rank] != nullptr,
+                    "mrb_als_peer_barrier: mrb_als_open_peers_all has not been called");
+        // a caller's stream first joins everything this problem has put on its own streams
+        // (uploads, pushes to the peers, grouped copies), so the barrier covers them
+        cudaStream_t s = on_problem_stream ? p->impl.stream() : static_cast<cudaStream_t>(stream);
+        p->impl.order_after_inputs(s);
+        enqueue_peer_barrier(p->barrier_peers, p->rank, p->world, s);
+        return 0;
+    });
+}
+
+int mrb_peer_barrier_timed_out(void) {
+    int out = 0;
+    const int rc = guarded([&] {
+        out = peer_barrier_timed_out() ? 1 : 0;
+        return 0;
+    });
+    return rc < 0 ? rc : out;
+}
+
+int mrb_als_upload_factor_rows(mrb_als_problem* p, const double* user_factors,
+                               const double* item_factors, int u_lo, int u_hi, int i_lo, int i_hi) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        p->impl.upload_factor_rows(user_factors, item_factors, u_lo, u_hi, i_lo, i_hi);
+        return 0;
+    });
+}
+
+int mrb_als_download_factor_rows(mrb_als_problem* p, double* user_factors, double* item_factors,
+                                 int u_lo, int u_hi, int i_lo, int i_hi, void* stream) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        p->impl.download_factor_rows(user_factors, item_factors, u_lo, u_hi, i_lo, i_hi,
+                                     static_cast<cudaStream_t>(stream));
+        MRB_REQUIRE(!peer_barrier_timed_out(),
+                    "a peer barrier timed out: a rank of the group did not arrive");
+        return 0;
+    });
+}
+
+int mrb_als_create_slice(const int* user_ids_slice, const int* item_ids_slice,
+                         const double* ratings_slice, int slice_begin, int slice_len,
+                         int num_ratings, int num_item_factors, int num_users, int num_items,
+                         mrb_als_problem** out) {
+    return guarded([&] {
+        MRB_REQUIRE(out != nullptr && slice_len >= 0, "mrb_als_create_slice: bad arguments");
+        *out = new mrb_als_problem(user_ids_slice, item_ids_slice, num_ratings, ratings_slice,
+                                   num_item_factors, num_users, num_items, slice_begin, slice_len);
+        return 0;
+    });
+}
+
+int mrb_als_set_shard_partition(mrb_als_problem* p, int rank, int world, int partition) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        p->rank = rank;
+        p->world = world;
+        p->impl.set_shard(rank, world, partition);
+        p->impl.half_sweep_prepare();
         return 0;
     });
 }

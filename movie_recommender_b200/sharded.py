@@ -2,9 +2,10 @@
 plumbing (rendezvous, the stream-ordered barrier, max-over-ranks timing), hand-written CUDA for
 everything on the data path.
 
-Partitioning: users, then movies, are cut into ``world`` contiguous row ranges holding ~nnz/world
-ratings each; every rank keeps the whole COO, both groupings and full replicas of both factor
-matrices (C3: 2 GB per GPU), only the WORK is sharded.  Exchange: the one place the path shards is
+Partitioning: the degree-sorted users, then movies, are dealt over the ``world`` ranks (or cut
+into contiguous cost-balanced ranges for the NCCL baseline); every rank keeps the whole COO,
+both groupings and full replicas of both factor matrices (C3: 2 GB per GPU), only the WORK is
+sharded.  Exchange: the one place the path shards is
 the all-gather of the freshly solved factor rows after each half-sweep.  Two implementations:
 
 * ``exchange="p2p"`` (default, the product): the solve kernel stores every solved row into all
@@ -27,9 +28,26 @@ class _DevArray:
                                          "version": 3, "strides": None}
 
 
+def io_slice(n, rank, world):
+    """Contiguous 1/world share of n items that rank moves across its host link."""
+    return n * rank // world, n * (rank + 1) // world
+
+
 class ShardedAls:
+    """One ALS problem over ``world`` GPUs (this process drives GPU ``rank``).
+
+    ``exchange="p2p"`` (the product).  Host traffic: every rank uploads only its 1/world slice
+    of the COO and of the initial factors and pushes it to the peers over NVLink (copy engines,
+    CUDA IPC mappings), so every byte crosses the box's host memory system once.  Work: the
+    degree-sorted rows are dealt over the ranks (``partition=1``; rows are stored individually
+    into every replica, so ownership need not be contiguous).  Exchange: fused into the solve
+    kernel (peer stores).  Synchronisation: a device-side flag barrier over the same mappings
+    (``peer.cu``), enqueued on the stream -- no host round trip, no library collective on the
+    data path.  ``exchange="nccl"`` is the baseline: full upload per rank, contiguous ranges,
+    ``all_gather`` of the ranges after each half-sweep."""
+
     def __init__(self, problem, k, num_users, num_items, rank, world, exchange="p2p",
-                 async_upload=False):
+                 async_upload=False, partition=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -37,28 +55,47 @@ class ShardedAls:
         self.nu, self.ni = num_users, num_items
         self.exchange = exchange
         self.nnz = len(problem["ratings"])
+        self.partition = (1 if exchange == "p2p" else 0) if partition is None else partition
         import os
         import time
         marks = [("start", time.time())]
-        self.prob = cpp_ls.AlsProblem(problem["user_ids"], problem["item_ids"], problem["ratings"],
-                                      k, num_users, num_items)
-        marks.append(("problem", time.time()))
-        # async_upload: the factors ride the copy stream behind the ratings (the caller keeps
-        # problem["*_factors0"] alive and untouched until the first get_factors)
-        self.prob.set_factors(problem["user_factors0"], problem["item_factors0"],
-                              wait=not async_upload)
-        marks.append(("set_factors", time.time()))
-        self.ranges = self.prob.set_shard(rank, world)
-        marks.append(("set_shard", time.time()))
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.flag = torch.zeros(1, device=self.device)
+        self.u_rows = io_slice(num_users, rank, world)
+        self.i_rows = io_slice(num_items, rank, world)
         if exchange == "p2p":
-            handles = [None] * world
-            dist.all_gather_object(handles, self.prob.ipc_handles())
+            self.prob = cpp_ls.AlsProblem(problem["user_ids"], problem["item_ids"], problem["ratings"],
+                                          k, num_users, num_items,
+                                          coo_slice=io_slice(self.nnz, rank, world))
+            marks.append(("create (slice upload enqueued)", time.time()))
+            mine = torch.frombuffer(bytearray(self.prob.ipc_handles_all()), dtype=torch.uint8).to(self.device)
+            allh = torch.empty(384 * world, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, mine)
+            allh = bytes(allh.cpu().numpy())
             marks.append(("handle exchange", time.time()))
-            self.prob.open_peers([h[0] for h in handles], [h[1] for h in handles], rank)
-            marks.append(("open_peers", time.time()))
+            self.prob.open_peer_group([allh[384 * r:384 * (r + 1)] for r in range(world)], rank,
+                                      self.partition)
+            marks.append(("open peers", time.time()))
+            self.prob.push_coo()            # own slice -> every peer (NVLink)
+            self.prob.peer_barrier()        # problem stream: every rank's slice is everywhere
+            uf0 = problem["user_factors0"].reshape(-1)
+            itf0 = problem["item_factors0"].reshape(-1)
+            self.prob.upload_factor_rows(uf0, itf0, *self.u_rows, *self.i_rows)
+            self.prob.build_index()         # id check, both groupings, this rank's work lists
+            marks.append(("index + work lists", time.time()))
+            # second barrier, on the stream the sweeps use and behind this rank's factor pushes:
+            # past it every replica holds the complete initial factors
+            self.prob.peer_barrier(torch.cuda.current_stream().cuda_stream)
+            self.ranges = None
         else:
+            self.prob = cpp_ls.AlsProblem(problem["user_ids"], problem["item_ids"], problem["ratings"],
+                                          k, num_users, num_items)
+            marks.append(("problem", time.time()))
+            # async_upload: the factors ride the copy stream behind the ratings (the caller keeps
+            # problem["*_factors0"] alive and untouched until the first get_factors)
+            self.prob.set_factors(problem["user_factors0"], problem["item_factors0"],
+                                  wait=not async_upload)
+            self.prob.set_shard_partition(rank, world, 0)
+            self.ranges = self.prob.shard_ranges()
             pu, pi = self.prob.device_factors()
             self.uf = torch.as_tensor(_DevArray(pu, num_users * (k + 1)), device=self.device)
             self.itf = torch.as_tensor(_DevArray(pi, num_items * k), device=self.device)
@@ -66,20 +103,21 @@ class ShardedAls:
             dist.all_gather_object(all_ranges, self.ranges)
             self.u_views = [self.uf[r[0] * (k + 1):r[1] * (k + 1)] for r in all_ranges]
             self.i_views = [self.itf[r[2] * k:r[3] * k] for r in all_ranges]
-        # past the barrier the peers may store solved rows into this rank's replicas: its own
-        # (possibly still running) factor upload must have landed before that
-        self.prob.finish_uploads()
-        dist.barrier()
-        marks.append(("barrier", time.time()))
+            self.prob.finish_uploads()
+            dist.barrier()
+        marks.append(("ready", time.time()))
         if rank == 0 and os.environ.get("MRB_E2E_TIMING"):
             import sys
             print("[ShardedAls] " + ", ".join("%s %.1f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3)
                                               for i in range(1, len(marks))), file=sys.stderr)
 
-    def _exchange(self, user_side):
+    def close(self):
+        self.prob.close()
+
+    def _exchange(self, user_side, stream):
         if self.exchange == "p2p":
             # rows are already in every replica; wait until every rank's kernel has finished
-            self.dist.all_reduce(self.flag)
+            self.prob.peer_barrier(stream)
         else:
             views = self.u_views if user_side else self.i_views
             self.dist.all_gather(views, views[self.rank])
@@ -87,9 +125,9 @@ class ShardedAls:
     def sweep(self):
         stream = self.torch.cuda.current_stream().cuda_stream
         self.prob.half_sweep(True, stream)
-        self._exchange(True)
+        self._exchange(True, stream)
         self.prob.half_sweep(False, stream)
-        self._exchange(False)
+        self._exchange(False, stream)
 
     def sse(self):
         """Training sum of squared errors after the last sweep, summed over ranks."""
@@ -98,6 +136,12 @@ class ShardedAls:
                               device=self.device)
         self.dist.all_reduce(t)
         return float(t.item())
+
+    def download_own_rows(self, user_factors, item_factors):
+        """This rank's I/O rows of the (replicated, complete) factor matrices into full-size
+        host arrays; the union over ranks is the whole result."""
+        stream = self.torch.cuda.current_stream().cuda_stream
+        self.prob.download_factor_rows(user_factors, item_factors, *self.u_rows, *self.i_rows, stream)
 
     def bench(self, algorithm, warmup, steps, sampler=None):
         torch, dist = self.torch, self.dist
@@ -124,8 +168,11 @@ class ShardedAls:
         wall_ms = (time.time() - t0) * 1e3
         if sampler is not None:
             sampler.mark_end()
-        ms = torch.tensor([e0.elapsed_time(e1), self.prob.collect_gram_ms()], dtype=torch.float64,
-                          device=self.device)
+        my_gram = self.prob.collect_gram_ms()
+        ms = torch.tensor([e0.elapsed_time(e1), my_gram], dtype=torch.float64, device=self.device)
+        per_rank = torch.zeros(self.world, dtype=torch.float64, device=self.device)
+        per_rank[self.rank] = my_gram / (2.0 * steps)
+        dist.all_reduce(per_rank)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)     # device time = max over ranks
         launches = cpp_ls.kernel_launches() - launches0
         sse = self.sse()
@@ -146,15 +193,18 @@ class ShardedAls:
         clocks = sampler.stop() if sampler is not None else None
         return dict(device_ms=float(ms[0]), gram_ms=float(ms[1]), wall_ms=wall_ms, clocks=clocks,
                     launches=int(launches) * self.world, user_factors=uf, item_factors=itf,
-                    sse=sse, exchange=self.exchange, ranges=self.ranges)
+                    sse=sse, exchange=self.exchange, ranges=self.ranges,
+                    per_rank_gram_ms=[round(float(v), 4) for v in per_rank.cpu()])
 
 
 def e2e_steps(problem, k, num_users, num_items, rank, world, steps, exchange="p2p", timing=False):
-    """End-to-end time of one sharded sweep from HOST buffers, per step: every rank uploads the
-    ratings and factors, builds its indices and work lists, maps the peers' factor buffers, runs
-    one sweep and copies the factors back INTO `problem["user_factors0"/"item_factors0"]` (pass
-    page-locked arrays: a pageable 137 MB copy each way costs more than the sweep).  Returns
-    seconds per step (max over ranks) and the factor arrays."""
+    """End-to-end time of one sharded sweep from HOST buffers, per step: every rank uploads its
+    1/world slice of the ratings and of the factors (pushed on to the peers over NVLink), builds
+    the indices and its work lists, runs one sweep and copies its 1/world share of the factor
+    rows back INTO `problem["user_factors0"/"item_factors0"]` (pass page-locked arrays).  After a
+    step the union of the ranks' host rows is the complete result, and it is what the next step
+    uploads.  Returns a dict: seconds per step (max over ranks), bytes moved per step over all
+    ranks, a description of the call."""
     import time
 
     import torch
@@ -162,6 +212,7 @@ def e2e_steps(problem, k, num_users, num_items, rank, world, steps, exchange="p2
     times = []
     uf_host = problem["user_factors0"].reshape(-1)
     itf_host = problem["item_factors0"].reshape(-1)
+    nnz = len(problem["ratings"])
     for step in range(steps + 1):              # step 0 is a warm-up
         dist.barrier()
         torch.cuda.synchronize()
@@ -170,21 +221,31 @@ def e2e_steps(problem, k, num_users, num_items, rank, world, steps, exchange="p2
                        async_upload=True)
         t1 = time.time()
         s.sweep()
-        torch.cuda.synchronize()
-        dist.barrier()
+        if exchange == "p2p":
+            s.download_own_rows(uf_host, itf_host)      # synchronises the stream
+        else:
+            torch.cuda.synchronize()
+            s.prob.get_factors(uf_host, itf_host)
         t2 = time.time()
-        s.prob.get_factors(uf_host, itf_host)
-        t3 = time.time()
-        dt = torch.tensor([t3 - t0], dtype=torch.float64, device=s.device)
+        dt = torch.tensor([t2 - t0], dtype=torch.float64, device=s.device)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        s.prob.close()
+        s.close()
         if timing and rank == 0:
             import sys
-            print("[e2e N=%d step %d] setup %.1f ms, sweep+barrier %.1f ms, get_factors %.1f ms" % (
-                world, step, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3), file=sys.stderr)
+            print("[e2e N=%d step %d] setup %.1f ms, sweep + download %.1f ms" % (
+                world, step, (t1 - t0) * 1e3, (t2 - t1) * 1e3), file=sys.stderr)
         if step > 0:
             times.append(float(dt.item()))
-    return sum(times) / len(times), uf_host, itf_host
+    fbytes = (num_users * (k + 1) + num_items * k) * 8
+    mult = 1 if exchange == "p2p" else world
+    return dict(sec_per_step=sum(times) / len(times), steps=len(times),
+                h2d_bytes_per_step=mult * (nnz * 16 + fbytes), d2h_bytes_per_step=mult * fbytes,
+                call="sharded.ShardedAls(host buffers) + one sweep + factor download per step on "
+                     "every rank; each rank moves its 1/%d slice of the ratings and factors across "
+                     "its host link, slices are exchanged over NVLink (peer copies), index build, "
+                     "work lists and peer mapping exchange included" % world
+                if exchange == "p2p" else
+                "ShardedAls(exchange='nccl'): every rank uploads everything")
 
 
 # ----------------------------------------------------------------------------------------------

@@ -142,10 +142,10 @@ def movie_medians(item_ids, raw_ratings, num_items):
     return med
 
 
-def planted_ratings(user_ids, item_ids, num_users, num_items, seed=DEFAULT_SEED, rank=8,
-                    noise=0.4, subtract_median=True):
-    """Ratings from a planted rank-``rank`` model + user bias + N(0, noise), rounded to 0.5
-    steps in [0.5, 5]; then minus the per-movie median (what ``cpp_ls.als`` is fed)."""
+def _planted_raw(user_ids, item_ids, num_users, num_items, seed, rank, noise, noise_rng=None):
+    """Raw (0.5-step) ratings of the planted model for the given pairs.  The model parameters
+    are the first four draws of rng(seed + 1); the noise follows on the same generator unless
+    ``noise_rng`` supplies another one (held-out pairs)."""
     rng = np.random.default_rng(seed + 1)
     pu = rng.standard_normal((num_users, rank)) * (0.9 / np.sqrt(rank))
     pv = rng.standard_normal((num_items, rank))
@@ -158,11 +158,55 @@ def planted_ratings(user_ids, item_ids, num_users, num_items, seed=DEFAULT_SEED,
         u = user_ids[s:s + step]
         i = item_ids[s:s + step]
         raw[s:s + step] = 3.4 + bias[u] + item_off[i] + np.einsum("ij,ij->i", pu[u], pv[i])
-    raw += rng.standard_normal(n) * noise
-    raw = np.clip(np.round(raw * 2.0) / 2.0, 0.5, 5.0)
+    raw += (rng if noise_rng is None else noise_rng).standard_normal(n) * noise
+    return np.clip(np.round(raw * 2.0) / 2.0, 0.5, 5.0)
+
+
+def planted_ratings(user_ids, item_ids, num_users, num_items, seed=DEFAULT_SEED, rank=8,
+                    noise=0.4, subtract_median=True):
+    """Ratings from a planted rank-``rank`` model + user bias + N(0, noise), rounded to 0.5
+    steps in [0.5, 5]; then minus the per-movie median (what ``cpp_ls.als`` is fed)."""
+    raw = _planted_raw(user_ids, item_ids, num_users, num_items, seed, rank, noise)
     if not subtract_median:
         return raw
     return raw - movie_medians(item_ids, raw, num_items)[item_ids]
+
+
+def heldout_ratings(train_user_ids, train_item_ids, num_users, num_items, count,
+                    seed=DEFAULT_SEED, rank=8, noise=0.4, medians=None):
+    """``count`` (user, movie) pairs that are NOT in the training set, drawn from the same
+    activity / popularity laws and rated by the same planted model (fresh noise), minus the
+    TRAINING set's movie medians -- the test split the reference evaluates on is prepared the
+    same way (python/full_data/movie_lens_data.py: medians come from the training set).
+    Returns ``(user_ids int32, item_ids int32, ratings f64)`` sorted by (user, movie)."""
+    nu, ni = int(num_users), int(num_items)
+    rng0 = np.random.default_rng(seed)           # the same two shuffles as rating_pairs
+    wu = np.cumsum(_power_weights(nu, 0.6, 20.0, rng0))
+    wi = np.cumsum(_power_weights(ni, 0.9, 30.0, rng0))
+    rng = np.random.default_rng(seed + 6)
+    train_keys = train_user_ids.astype(np.int64) * ni + train_item_ids
+    if len(train_keys) > 1 and np.any(train_keys[1:] < train_keys[:-1]):
+        train_keys = np.sort(train_keys)
+    keys = np.zeros(0, dtype=np.int64)
+    for _ in range(100):
+        missing = int(count) - len(keys)
+        if missing <= 0:
+            break
+        m = int(missing * 1.25) + 64
+        u = np.minimum(np.searchsorted(wu, rng.random(m)), nu - 1).astype(np.int64)
+        i = np.minimum(np.searchsorted(wi, rng.random(m)), ni - 1).astype(np.int64)
+        cand = _not_in_sorted(_not_in_sorted(_sorted_unique(u * ni + i), train_keys), keys)
+        if len(cand) > missing:
+            cand = np.sort(cand[rng.permutation(len(cand))[:missing]])
+        keys = np.sort(np.concatenate([keys, cand]), kind="stable")
+    hu = (keys // ni).astype(np.int32)
+    hi = (keys - (keys // ni) * ni).astype(np.int32)
+    med = medians
+    if med is None:
+        raw_train = _planted_raw(train_user_ids, train_item_ids, nu, ni, seed, rank, noise)
+        med = movie_medians(train_item_ids, raw_train, ni)
+    raw = _planted_raw(hu, hi, nu, ni, seed, rank, noise, noise_rng=rng)
+    return hu, hi, raw - med[hi]
 
 
 def initial_factors(num_users, num_items, k, seed=DEFAULT_SEED):
@@ -174,21 +218,30 @@ def initial_factors(num_users, num_items, k, seed=DEFAULT_SEED):
 
 
 def als_problem(num_users, num_items, num_ratings, k, seed=DEFAULT_SEED, min_degrees=True,
-                shuffle=False):
+                shuffle=False, heldout=0):
     """One ALS training problem of the given shape: dict with the COO triples, k and U(-1,1)
     initial factors.  ``shuffle=True`` randomises the COO order (the order cpp_ls_test.py
-    feeds, cpp/python/cpp_ls_test.py:110-116) instead of the trainer's grouped-by-user order."""
+    feeds, cpp/python/cpp_ls_test.py:110-116) instead of the trainer's grouped-by-user order.
+    ``heldout=N`` adds N held-out ratings of the same model (``heldout_user_ids`` ...)."""
     u, i = rating_pairs(num_users, num_items, num_ratings,
                         min_user_deg=(k + 1 if min_degrees else 0),
                         min_item_deg=(k if min_degrees else 0), seed=seed)
-    r = planted_ratings(u, i, num_users, num_items, seed=seed)
+    raw = planted_ratings(u, i, num_users, num_items, seed=seed, subtract_median=False)
+    med = movie_medians(i, raw, num_items)
+    r = raw - med[i]
+    held = None
+    if heldout:
+        held = heldout_ratings(u, i, num_users, num_items, heldout, seed=seed, medians=med)
     if shuffle:
         perm = np.random.default_rng(seed + 3).permutation(len(u))
         u, i, r = u[perm], i[perm], r[perm]
     uf, itf = initial_factors(num_users, num_items, k, seed=seed)
-    return dict(user_ids=np.ascontiguousarray(u), item_ids=np.ascontiguousarray(i),
-                ratings=np.ascontiguousarray(r), k=k, num_users=num_users, num_items=num_items,
-                user_factors0=uf, item_factors0=itf)
+    out = dict(user_ids=np.ascontiguousarray(u), item_ids=np.ascontiguousarray(i),
+               ratings=np.ascontiguousarray(r), k=k, num_users=num_users, num_items=num_items,
+               user_factors0=uf, item_factors0=itf)
+    if held is not None:
+        out.update(heldout_user_ids=held[0], heldout_item_ids=held[1], heldout_ratings=held[2])
+    return out
 
 
 def bias_model_system(user_ids, item_ids, raw_ratings, num_users, num_items, seed=DEFAULT_SEED):

@@ -20,7 +20,8 @@ from movie_recommender_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def test_two_emulated_ranks_match_single_gpu_bitwise(require_gpu, cpp_ls):
+@pytest.mark.parametrize("partition", [0, 1])
+def test_two_emulated_ranks_match_single_gpu_bitwise(require_gpu, cpp_ls, partition):
     nu, ni, nnz, k = 3000, 900, 150000, 20
     p = synth.als_problem(nu, ni, nnz, k, seed=77)
     args = (p["user_ids"], p["item_ids"], p["ratings"], k, nu, ni)
@@ -31,9 +32,13 @@ def test_two_emulated_ranks_match_single_gpu_bitwise(require_gpu, cpp_ls):
         ranges = []
         for r, prob in enumerate(ranks):
             prob.set_factors(p["user_factors0"], p["item_factors0"])
-            ranges.append(prob.set_shard(r, 2))
-        assert ranges[0][0] == 0 and ranges[0][1] == ranges[1][0] and ranges[1][1] == nu
-        assert ranges[0][2] == 0 and ranges[0][3] == ranges[1][2] and ranges[1][3] == ni
+            prob.set_shard_partition(r, 2, partition)
+            ranges.append(prob.shard_ranges())
+        if partition == 0:      # contiguous cost-balanced ranges that tile the rows
+            assert ranges[0][0] == 0 and ranges[0][1] == ranges[1][0] and ranges[1][1] == nu
+            assert ranges[0][2] == 0 and ranges[0][3] == ranges[1][2] and ranges[1][3] == ni
+        else:                   # dealt: every rank draws from the whole degree-sorted list
+            assert ranges[0] == ranges[1] == (0, nu, 0, ni)
         ptrs = [prob.device_factors() for prob in ranks]
         for prob in ranks:
             prob.set_peer_pointers([q[0] for q in ptrs], [q[1] for q in ptrs])
@@ -81,7 +86,28 @@ for mode in ("p2p", "nccl"):
         assert np.array_equal(itf.view(np.uint64), ref[1].view(np.uint64)), mode
         print("mode", mode, "ok")
     dist.barrier()
-    s.prob.close()
+    s.close()
+# end to end from host buffers: every rank uploads 1/world of the COO and of the factors, runs
+# one sweep per step, downloads its 1/world share of the rows; the union must be the one-GPU bits
+host = dict(p)
+host["user_factors0"] = p["user_factors0"].copy()
+host["item_factors0"] = p["item_factors0"].copy()
+res = sharded.e2e_steps(host, k, nu, ni, rank, world, 2)       # warm-up + 2 steps = 3 sweeps
+assert res["steps"] == 2 and res["h2d_bytes_per_step"] == nnz * 16 + (nu * (k + 1) + ni * k) * 8
+ub, ib = sharded.io_slice(nu, rank, world), sharded.io_slice(ni, rank, world)
+mine_u = torch.from_numpy(host["user_factors0"][ub[0] * (k + 1):ub[1] * (k + 1)].copy())
+mine_i = torch.from_numpy(host["item_factors0"][ib[0] * k:ib[1] * k].copy())
+parts_u, parts_i = [None] * world, [None] * world
+dist.all_gather_object(parts_u, mine_u.numpy())
+dist.all_gather_object(parts_i, mine_i.numpy())
+if rank == 0:
+    ref = cpp_ls.als(p["user_ids"], p["item_ids"], p["ratings"], k, nu, ni, -1e300, 3, 4,
+                     user_factors=p["user_factors0"], item_factors=p["item_factors0"])
+    assert np.array_equal(np.concatenate(parts_u).view(np.uint64), ref[0].view(np.uint64))
+    assert np.array_equal(np.concatenate(parts_i).view(np.uint64), ref[1].view(np.uint64))
+    assert cpp_ls._dll.mrb_peer_barrier_timed_out() == 0
+    print("mode e2e ok")
+dist.barrier()
 dist.destroy_process_group()
 '''
 
@@ -96,4 +122,4 @@ def test_two_processes_two_gpus(require_gpu, tmp_path):
                           "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
                           "29533", str(script)], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("ok") == 2
+    assert out.stdout.count("ok") == 3

@@ -35,6 +35,19 @@ for r in allr:
     ci = (iptr[r[3]] - iptr[r[2]]) + 100 * (r[3] - r[2])
     assert abs(cu - (90000 + 100 * 3000) / world) < 0.05 * (90000 + 100 * 3000)
     assert abs(ci - (90000 + 100 * 700) / world) < 0.05 * (90000 + 100 * 700)
+# the product partition: degree-sorted rows dealt in snake order -- the ranks' shares are disjoint,
+# cover every row, and their cost is within 1 %% of the mean
+for ptr, rows, unit in ((uptr, 3000, 100), (iptr, 700, 100)):
+    own = cpp_ls.dealt_owners(ptr, rank, world)
+    alls = [None] * world
+    dist.all_gather_object(alls, own.tolist())
+    flat = np.concatenate([np.asarray(a, dtype=np.int64) for a in alls])
+    assert len(flat) == rows and len(np.unique(flat)) == rows
+    deg = np.diff(ptr)
+    assert np.all(np.diff(deg[own]) <= 0)          # longest processing time first
+    cost = float(deg[own].sum() + unit * len(own))
+    mean = (90000 + unit * rows) / world
+    assert abs(cost - mean) < 0.01 * mean, (cost, mean)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok", mine)
@@ -50,6 +63,17 @@ def test_shard_ranges_world2_gloo(tmp_path):
                           "29517", str(script)], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_dealt_owners_edge_cases():
+    ptr = np.array([0, 5, 5, 9, 20, 21, 40], dtype=np.int32)      # degrees 5 0 4 11 1 19
+    assert list(cpp_ls.dealt_owners(ptr, 0, 1)) == [5, 3, 0, 2, 4, 1]
+    # world 4: block 0 = [5 3 0 2] in plain order, incomplete block 1 = [4 1] to ranks 0, 1
+    got = [list(cpp_ls.dealt_owners(ptr, r, 4)) for r in range(4)]
+    assert got == [[5, 4], [3, 1], [0], [2]]
+    # world 2: blocks [5 3] [0 2] (snake: reversed) [4 1]
+    assert [list(cpp_ls.dealt_owners(ptr, r, 2)) for r in range(2)] == [[5, 2, 4], [3, 0, 1]]
+    assert list(cpp_ls.dealt_owners(np.zeros(1, dtype=np.int32), 0, 3)) == []
 
 
 def test_shard_ranges_edge_cases():
