@@ -40,6 +40,11 @@ namespace {
 
 constexpr int GRAM_SEG = 2048;     // ratings per work item
 constexpr int GRAM_WARPS = 4;      // warps per CTA
+// (Measured and rejected, profiles/ab_solve_r02.log: one CTA of 8 warps per SM whose two warps
+// per scheduler pass a "tensor token", so that one accumulates while the other solves -- a single
+// warp reaches only 64 % of the accumulation rate two warps reach together: 7.8 vs 6.6 ms.)
+template <bool USER>
+constexpr int gram_warps() { return GRAM_WARPS; }
 #ifndef GRAM_RING_USER
 #define GRAM_RING_USER 3           // fragment sets in flight, user half-sweep (gathers hit L2)
 #endif
@@ -51,7 +56,7 @@ constexpr int GRAM_WARPS = 4;      // warps per CTA
 #define GRAM_DEFAULT_ORDER 0
 #endif
 #ifndef GRAM_SOLVE_VARIANT
-#define GRAM_SOLVE_VARIANT 0       // 1: block-of-four pivot candidate (gram_solve.cuh), A/B builds only
+#define GRAM_SOLVE_VARIANT 3       // gram_solve.cuh: W = L_d^-T back substitution + tensor-core panel
 #endif
 
 // Element j of the augmented row [a; b] AS FETCHED: no arithmetic on a value that has just been
@@ -83,7 +88,10 @@ __device__ __forceinline__ int work_index(int w, int n_work, int mode) {
 __device__ double g_zero_row[64];   // zero-initialised: the factor row of a padding rating
 
 template <int M8, bool USER, int EPI>
-__global__ void __launch_bounds__(GRAM_WARPS * 32)
+#ifndef GRAM_MIN_CTAS
+#define GRAM_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(gram_warps<USER>() * 32, GRAM_MIN_CTAS)
 k_gram(const GramArgs A) {
     constexpr int ST = M8 * (M8 + 1) / 2;
     const int lane = threadIdx.x & 31;
@@ -757,18 +765,19 @@ void build_side_lists(Side& sd, const int* d_ptr, int owners, int nnz, int rank,
 template <int M8, bool USER, int EPI>
 void launch_gram(const GramArgs& a, int sms, cudaStream_t s) {
     auto kern = k_gram<M8, USER, EPI>;
+    constexpr int W = gram_warps<USER>();
     // one process drives one GPU model; the value is idempotent, so a benign race is excluded by
     // making the cache atomic
     static std::atomic<int> cached{0};
     int per_sm = cached.load(std::memory_order_relaxed);
     if (per_sm == 0) {
-        MRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GRAM_WARPS * 32, 0));
+        MRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, 0));
         cached.store(per_sm, std::memory_order_relaxed);
     }
     MRB_REQUIRE(per_sm >= 1, "gram kernel does not fit on an SM");
     // persistent CTAs: one wave that fills every SM, work items handed out dynamically
-    const int grid = std::min(sms * per_sm, ceil_div(a.n_work, GRAM_WARPS));
-    kern<<<grid > 0 ? grid : 1, GRAM_WARPS * 32, 0, s>>>(a); MRB_LAUNCHED(1);
+    const int grid = std::min(sms * per_sm, ceil_div(a.n_work, W));
+    kern<<<grid > 0 ? grid : 1, W * 32, 0, s>>>(a); MRB_LAUNCHED(1);
     MRB_CUDA(cudaGetLastError());
 }
 

@@ -107,6 +107,16 @@ MRB_DEVICE_INLINE double xor_sum_q(double v) {   // sum over the 4 lanes sharing
 // pivot falls below 1e-12 of the original diagonal get delta = 0 (they keep their previous value,
 // as they do under the reference's warm-started CG), the others are solved consistently.
 // ------------------------------------------------------------------------------------------
+// VARIANT 0: pivot columns eliminated over the whole tile column, scalar back substitution.
+// VARIANT 2: an identity tile rides through the pivot loop of every tile column and comes out as
+//   W = L_d^-T (the inverse transpose of the 8x8 diagonal factor; a skipped pivot leaves a zero
+//   column and a zero row), so the back substitution is ONE 8x8 matrix-vector product per tile
+//   row (7 dependent steps instead of 51).
+// VARIANT 3: additionally the panel below the diagonal tile stays out of the pivot loop and is
+//   formed afterwards as X W on the tensor cores (2 DMMA per tile, operands without shuffles via
+//   the even/odd column split, W^T by one fragment transpose).
+// (A block-of-four pivot variant was measured and rejected: 7.25 vs 6.63 ms on the user side of
+//  C3, profiles/ab_b4_r02.log.)
 template <int M8, int VARIANT = 0>
 MRB_DEVICE_INLINE void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], int n,
                                            double* __restrict__ xo, double* __restrict__ sse_slot,
@@ -178,106 +188,18 @@ MRB_DEVICE_INLINE void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], int n,
 #pragma unroll
     for (int t = 0; t < M8; t++) invd[t] = 0;
     double corner = 0;
-
-    if constexpr (VARIANT == 1) {
-        // ---- CANDIDATE (not the default; developed on the emulated warp, tests/emu): pivots in
-        // blocks of FOUR = the k of mma.m8n8k4.  Per block: the 4x4 diagonal block S and its four
-        // thresholds are broadcast to every lane; every lane factors S = L4 L4^T and forms
-        // W = L4^-T in registers (no shuffle inside the dependent chain; a skipped pivot has
-        // r = 0, which zeroes its column of L4 and of W); the block's columns of every tile of
-        // the tile column become P W with one DMMA (B operand picked from the lane's own W,
-        // placed in columns 4h .. 4h+3); every trailing update, the right half of the same tile
-        // column included (masked B operand), is a rank-4 DMMA.
+    constexpr bool WSUB = VARIANT >= 2;     // W = L_d^-T per tile column
+    constexpr bool WPANEL = VARIANT >= 3;   // panel = X W on the tensor cores
+    double Wt[WSUB ? M8 : 1][2];
+    if (WSUB) {
 #pragma unroll
-        for (int tk = 0; tk < M8; tk++) {
-            const int D = TI(tk, tk);
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                // warp-uniform: in the last tile column only the blocks up to the one holding
-                // index n (fragment row/column pr) exist
-                if (tk == M8 - 1 && 4 * h > pr) continue;
-                const int l0 = (4 * h) * 4 + 2 * h;          // lane (4h, 2h): row 4h, columns 4h, 4h+1
-                const double S00 = shfl_double(acc[D][0], l0);
-                const double S10 = shfl_double(acc[D][0], l0 + 4), S11 = shfl_double(acc[D][1], l0 + 4);
-                const double S20 = shfl_double(acc[D][0], l0 + 8), S21 = shfl_double(acc[D][1], l0 + 8);
-                const double S22 = shfl_double(acc[D][0], l0 + 9);
-                const double S30 = shfl_double(acc[D][0], l0 + 12), S31 = shfl_double(acc[D][1], l0 + 12);
-                const double S32 = shfl_double(acc[D][0], l0 + 13), S33 = shfl_double(acc[D][1], l0 + 13);
-                // threshold of column c = 4h + j sits on lane (c, c >> 1)
-                const double t0 = shfl_double(thr[tk], (4 * h + 0) * 4 + 2 * h);
-                const double t1 = shfl_double(thr[tk], (4 * h + 1) * 4 + 2 * h);
-                const double t2 = shfl_double(thr[tk], (4 * h + 2) * 4 + 2 * h + 1);
-                const double t3 = shfl_double(thr[tk], (4 * h + 3) * 4 + 2 * h + 1);
-                const bool last = tk == M8 - 1;
-                // local factorisation, identical on every lane
-                const double d0 = S00;
-                const bool ok0 = (!last || 4 * h + 0 < pr) && d0 > t0 && t0 > 1e-290;
-                const double r0 = ok0 ? fast_rsqrt(d0) : 0.0;
-                const double L10 = S10 * r0, L20 = S20 * r0, L30 = S30 * r0;
-                const double d1 = fma(-L10, L10, S11);
-                const bool ok1 = (!last || 4 * h + 1 < pr) && d1 > t1 && t1 > 1e-290;
-                const double r1 = ok1 ? fast_rsqrt(d1) : 0.0;
-                const double L21 = fma(-L20, L10, S21) * r1, L31 = fma(-L30, L10, S31) * r1;
-                const double d2 = fma(-L21, L21, fma(-L20, L20, S22));
-                const bool ok2 = (!last || 4 * h + 2 < pr) && d2 > t2 && t2 > 1e-290;
-                const double r2 = ok2 ? fast_rsqrt(d2) : 0.0;
-                const double L32 = fma(-L31, L21, fma(-L30, L20, S32)) * r2;
-                const double d3 = fma(-L32, L32, fma(-L31, L31, fma(-L30, L30, S33)));
-                const bool ok3 = (!last || 4 * h + 3 < pr) && d3 > t3 && t3 > 1e-290;
-                const double r3 = ok3 ? fast_rsqrt(d3) : 0.0;
-                if (last && (pr >> 2) == h) {
-                    const int j = pr & 3;
-                    corner = j == 0 ? d0 : (j == 1 ? d1 : (j == 2 ? d2 : d3));
-                }
-                // W = L4^-T, upper triangular: W[:,j] = (e_j - sum_{k<j} W[:,k] L4[j][k]) r_j
-                const double W00 = r0;
-                const double W01 = -(W00 * L10) * r1, W11 = r1;
-                const double W02 = -fma(W01, L21, W00 * L20) * r2, W12 = -(W11 * L21) * r2, W22 = r2;
-                const double W03 = -fma(W02, L32, fma(W01, L31, W00 * L30)) * r3;
-                const double W13 = -fma(W12, L32, W11 * L31) * r3, W23 = -(W22 * L32) * r3, W33 = r3;
-                // B operand of P W: lane (p, q) holds B[q][p] = W[q][p - 4h] inside the block
-                const int jj = p & 3;
-                const double w_q0 = jj == 0 ? W00 : (jj == 1 ? W01 : (jj == 2 ? W02 : W03));
-                const double w_q1 = jj == 0 ? 0.0 : (jj == 1 ? W11 : (jj == 2 ? W12 : W13));
-                const double w_q2 = jj < 2 ? 0.0 : (jj == 2 ? W22 : W23);
-                const double w_q3 = jj == 3 ? W33 : 0.0;
-                double bw = q == 0 ? w_q0 : (q == 1 ? w_q1 : (q == 2 ? w_q2 : w_q3));
-                const bool in_rows = (p >> 2) == h;
-                bw = in_rows ? bw : 0.0;
-                if (in_rows) invd[tk] = jj == 0 ? r0 : (jj == 1 ? r1 : (jj == 2 ? r2 : r3));
-                // the block's columns of the tile column: P <- P W; A fragments of the result
-                const int src = p * 4 + 2 * h + (q >> 1);       // lane holding X[p][4h + q]
-                const bool in_cols = (q >> 1) == h;
-                double ax[M8];
-#pragma unroll
-                for (int ti = tk; ti < M8; ti++) {
-                    const int X = TI(ti, tk);
-                    const double v0 = shfl_double(acc[X][0], src);
-                    const double v1 = shfl_double(acc[X][1], src);
-                    const double a_old = (q & 1) ? v1 : v0;
-                    double c0 = in_cols ? 0.0 : acc[X][0], c1 = in_cols ? 0.0 : acc[X][1];
-                    dmma884(c0, c1, a_old, bw);
-                    acc[X][0] = c0;
-                    acc[X][1] = c1;
-                    const double n0 = shfl_double(c0, src);
-                    const double n1 = shfl_double(c1, src);
-                    ax[ti] = (q & 1) ? n1 : n0;                  // L(ti,tk)[p][4h + q]
-                }
-                if (h == 0) {
-                    // right half of the same tile column: X[:, 4..7] -= L(ti)[:, 0..3] Ld[4..7, 0..3]^T
-                    const double bmask = (p >> 2) == 1 ? ax[tk] : 0.0;
-#pragma unroll
-                    for (int ti = tk; ti < M8; ti++)
-                        dmma884(acc[TI(ti, tk)][0], acc[TI(ti, tk)][1], -ax[ti], bmask);
-                }
-#pragma unroll
-                for (int ti = tk + 1; ti < M8; ti++)
-#pragma unroll
-                    for (int tj = tk + 1; tj <= ti; tj++)
-                        dmma884(acc[TI(ti, tj)][0], acc[TI(ti, tj)][1], -ax[ti], ax[tj]);
-            }
+        for (int t = 0; t < M8; t++) {
+            Wt[t][0] = p == 2 * q ? 1.0 : 0.0;
+            Wt[t][1] = p == 2 * q + 1 ? 1.0 : 0.0;
         }
-    } else {
+    }
+
+    {
         // The whole factorisation is branch-free per lane (selects on multipliers, never divergent
         // control flow around a shuffle) and keeps the pivot columns UNSCALED inside a tile column:
         //   X[p][c2] -= X[p][c] * (D[c2][c] / d_c)      for the 8 pivots c of the tile column,
@@ -309,11 +231,16 @@ MRB_DEVICE_INLINE void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], int n,
                             const double f0 = q > cp ? m0 * inv_d : 0.0;
                             const double f1 = (j == 0 ? q >= cp : q > cp) ? m1 * inv_d : 0.0;
     #pragma unroll
-                            for (int ti = tk; ti < M8; ti++) {
+                            for (int ti = tk; ti < (WPANEL ? tk + 1 : M8); ti++) {
                                 const int X = TI(ti, tk);
                                 const double xrc = shfl_double(acc[X][j], p * 4 + cp);   // X[p][c]
                                 acc[X][0] = fma(-xrc, f0, acc[X][0]);
                                 acc[X][1] = fma(-xrc, f1, acc[X][1]);
+                            }
+                            if (WSUB) {
+                                const double wrc = shfl_double(Wt[WSUB ? tk : 0][j], p * 4 + cp);
+                                Wt[WSUB ? tk : 0][0] = fma(-wrc, f0, Wt[WSUB ? tk : 0][0]);
+                                Wt[WSUB ? tk : 0][1] = fma(-wrc, f1, Wt[WSUB ? tk : 0][1]);
                             }
                         }
                     }
@@ -325,13 +252,42 @@ MRB_DEVICE_INLINE void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], int n,
                 const double r0 = shfl_double(invd[tk], (2 * q) * 4);
                 const double r1 = shfl_double(invd[tk], (2 * q + 1) * 4);
     #pragma unroll
-                for (int ti = tk; ti < M8; ti++) {
+                for (int ti = tk; ti < (WPANEL ? tk + 1 : M8); ti++) {
                     acc[TI(ti, tk)][0] *= r0;
                     acc[TI(ti, tk)][1] *= r1;
                 }
+                if (WSUB) {
+                    Wt[WSUB ? tk : 0][0] *= r0;
+                    Wt[WSUB ? tk : 0][1] *= r1;
+                }
+            }
+            if (WPANEL && tk < M8 - 1) {
+                // W^T as a C fragment: lane (p, q) slot s holds W[2q + s][p] -- which is element
+                // (k = q, column p) of the B operand over the rows {2q + s} of W
+                double wT[2];
+    #pragma unroll
+                for (int sl = 0; sl < 2; sl++) {
+                    const int src = (2 * q + sl) * 4 + (p >> 1);
+                    const double v0 = shfl_double(Wt[WSUB ? tk : 0][0], src);
+                    const double v1 = shfl_double(Wt[WSUB ? tk : 0][1], src);
+                    wT[sl] = (p & 1) ? v1 : v0;
+                }
+                // L(ti,tk) = X(ti,tk) W : contraction over X's columns, even ones then odd ones
+    #pragma unroll
+                for (int ti = tk + 1; ti < M8; ti++) {
+                    const int X = TI(ti, tk);
+                    double c0 = 0.0, c1 = 0.0;
+                    dmma884(c0, c1, acc[X][0], wT[0]);
+                    dmma884(c0, c1, acc[X][1], wT[1]);
+                    acc[X][0] = c0;
+                    acc[X][1] = c1;
+                }
             }
             if (tk < M8 - 1) {
-                // trailing update on the tensor cores
+                // trailing update on the tensor cores: T(ti,tj) -= L(ti,tk) L(tj,tk)^T
+    #ifdef GRAM_SOLVE_NATURAL_K
+                // contraction index in natural order (columns 0..3, then 4..7): the C fragments
+                // have to be converted to A / B fragments with two shuffles per 8x4 chunk
                 double ax[M8][2];
     #pragma unroll
                 for (int ti = tk + 1; ti < M8; ti++)
@@ -342,6 +298,19 @@ MRB_DEVICE_INLINE void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], int n,
                         const double v1 = shfl_double(acc[TI(ti, tk)][1], src);
                         ax[ti][h] = (q & 1) ? v1 : v0;   // L(ti,tk)[p][4h+q]
                     }
+    #else
+                // the contraction runs over the panel's 8 columns in any order, as long as both
+                // operands agree: take the EVEN columns in one mma and the ODD ones in the other.
+                // Lane (p, q) holds L[p][2q + h] in slot h of the C fragment, which is exactly
+                // element (row p, k = q) of an A fragment and (k = q, column p) of a B fragment
+                // over the columns {2q + h}: no data movement at all.
+                double ax[M8][2];
+    #pragma unroll
+                for (int ti = tk + 1; ti < M8; ti++) {
+                    ax[ti][0] = acc[TI(ti, tk)][0];
+                    ax[ti][1] = acc[TI(ti, tk)][1];
+                }
+    #endif
     #pragma unroll
                 for (int ti = tk + 1; ti < M8; ti++)
     #pragma unroll
@@ -363,6 +332,29 @@ MRB_DEVICE_INLINE void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], int n,
     double part[M8][2];
 #pragma unroll
     for (int t = 0; t < M8; t++) { part[t][0] = 0; part[t][1] = 0; }
+    if (WSUB) {
+        // delta_tj = W_tj (y_tj - sum_{ti > tj} L(ti,tj)^T delta_ti): one 8x8 matrix-vector
+        // product per tile row.  W's zero columns / rows (skipped pivots, the indices >= n of the
+        // last tile) make the corresponding delta exactly 0.
+#pragma unroll
+        for (int tj = M8 - 1; tj >= 0; tj--) {
+            double yv[2];
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                yv[s] = shfl_double(acc[TI(TN, tj)][s], pr * 4 + q);
+                if (tj < M8 - 1) yv[s] -= xor_sum_p(part[tj][s]);
+            }
+            const int wt = WSUB ? tj : 0;
+            const double dp = xor_sum_q(fma(Wt[wt][0], yv[0], Wt[wt][1] * yv[1]));   // delta[8 tj + p]
+#pragma unroll
+            for (int t2 = 0; t2 < tj; t2++) {
+                part[t2][0] = fma(acc[TI(tj, t2)][0], dp, part[t2][0]);
+                part[t2][1] = fma(acc[TI(tj, t2)][1], dp, part[t2][1]);
+            }
+            xq[tj][0] += shfl_double(dp, (2 * q) * 4);
+            xq[tj][1] += shfl_double(dp, (2 * q + 1) * 4);
+        }
+    } else {
 #pragma unroll
     for (int tj = M8 - 1; tj >= 0; tj--) {
         const int D = TI(tj, tj);
@@ -404,6 +396,7 @@ MRB_DEVICE_INLINE void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], int n,
         }
         xq[tj][0] += dlt[0];
         xq[tj][1] += dlt[1];
+    }
     }
     if (p == 0) {
 #pragma unroll

@@ -52,8 +52,12 @@ int dispatch(int m8, int n, const double* aug, int ld, double* x, double* sse) {
 }
 }  // namespace
 
-// variant 0: the solve the kernel uses; variant 1: the block-of-four candidate
+// variants of gram_solve (csrc/gram_solve.cuh): 0 scalar back substitution, 2 W = L_d^-T per
+// tile column, 3 panel formed on the tensor cores as well
 extern "C" int emu_gram_solve(int variant, int m8, int n, const double* aug, int ld, double* x,
                               double* sse) {
-    return variant == 0 ? dispatch<0>(m8, n, aug, ld, x, sse) : dispatch<1>(m8, n, aug, ld, x, sse);
+    if (variant == 0) return dispatch<0>(m8, n, aug, ld, x, sse);
+    if (variant == 2) return dispatch<2>(m8, n, aug, ld, x, sse);
+    if (variant == 3) return dispatch<3>(m8, n, aug, ld, x, sse);
+    return -3;
 }

@@ -15,7 +15,7 @@ from conftest import ROOT
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["kernel", "block4-candidate"])
+@pytest.fixture(scope="module", params=[0, 2, 3], ids=["scalar-backsub", "W-backsub", "W-backsub+mma-panel"])
 def emu(request):
     variant = request.param
     subprocess.run(["make", "-C", EMU_DIR], check=True, capture_output=True)
