@@ -33,7 +33,7 @@ contract for their own metric; they live in tools/bench_configs.py.
                     start on C3, and on C1 with the unmodified reference at T=1 and T=cores beside
                     them (its own reproducibility floor) -- BASELINE.md section 3.
 * ``cpu_baseline``: the UNMODIFIED reference library (oracle/_ref/cpp_ls_lib.so) on the host
-                    cores, one sweep over a 10 % user subsample of the same workload with the
+                    cores, one sweep over a 20 % user subsample of the same workload with the
                     reference's shrink rule re-applied (movies >= k, users >= k+1 ratings).
 * ``--impl reference`` times only that reference arm (rank 0) and prints its own line.
 
@@ -261,6 +261,9 @@ def shrunk_user_subsample(p, w, fraction):
         if nk.sum() == keep.sum():
             break
         keep = nk
+    if not keep.any():          # tiny development workloads: nothing survives, keep the prefix
+        keep[:] = True
+        rounds = 0
     u, i, r = u[keep], i[keep], r[keep]
     users, u_new = np.unique(u, return_inverse=True)
     items, i_new = np.unique(i, return_inverse=True)
@@ -275,7 +278,8 @@ def shrunk_user_subsample(p, w, fraction):
 def sample_description(s, w):
     return ("%.0f %% user subsample of the workload with the reference's shrink rule re-applied "
             "(first %d users / %d ratings -> %d users x %d movies, %d ratings after %d shrink "
-            "round(s); the full C3 sweep needs ~34 GB and minutes per sweep on the host), one "
+            "round(s): every movie keeps >= k and every user >= k+1 ratings, as in the full "
+            "workload; the full C3 sweep needs ~34 GB and minutes per sweep on the host), one "
             "sweep per step, als_from_python(max_iteration=1) carried over" %
             (100 * s["fraction"], s["users_before"], s["ratings_before"], s["num_users"],
              s["num_items"], len(s["ratings"]), s["shrink_rounds"]))
@@ -433,7 +437,7 @@ def main():
                     help="4 = gathered Gram + Cholesky (north-star path, default); 1 = the "
                          "reference's CG, bit-faithful; 3 = the same CG on Gram blocks")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-sample-fraction", type=float, default=0.10)
+    ap.add_argument("--cpu-sample-fraction", type=float, default=0.20)
     ap.add_argument("--parity-sweeps", type=int, default=10)
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity tail")
     ap.add_argument("--seed", type=int, default=20181001)

@@ -313,6 +313,24 @@ MRB_API int mrb_als_shrink(const int* user_slot_ids, const int* movie_ids, const
                            int* keep_pos_out, int* user_new_id, int* movie_new_id,
                            mrb_shrink_info* info);
 
+/* ------------------------------------------------------------------------------------------
+ * 9. Extensions: per-user evaluation of a trained model.
+ *    Replaces the loop of _als_eval (python/full_data/worker_process.py:262-306): for every test
+ *    rating the prediction of ALS_Model.predict (python/full_data/als_predictor.py:35-60, same
+ *    arithmetic order: sequential sum of products, + user bias, + movie median), then
+ *    compute_ranking_agreement (python/full_data/my_util.py:101-145) as exact pair counts:
+ *    agree[u] / (agree[u] + disagree[u]) over the pairs of user u's test movies whose actual
+ *    ratings differ.  Entries are grouped by user (user_ptr, CSR); entry_user_row / entry_movie_row
+ *    index the factor arrays, -1 = the reference makes no prediction for that entry (dropped);
+ *    n_pred[u] = entries of user u with a prediction (the reference needs > 1).
+ * ---------------------------------------------------------------------------------------- */
+MRB_API int mrb_als_rank_agreement(const int* user_ptr, int num_users, const int* entry_user_row,
+                                   const int* entry_movie_row, const double* actual,
+                                   const double* median, const double* user_factors,
+                                   int num_user_rows, const double* item_factors, int num_items,
+                                   int num_item_factors, long long* agree, long long* disagree,
+                                   int* n_pred, float* kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -155,6 +155,10 @@ def _declare(dll):
     dll.mrb_als_shrink.restype = c_int
     dll.mrb_als_shrink.argtypes = [_I, _I, _D, c_int, c_int, c_int, _D, c_int, c_int, _I, _I, _D,
                                    _I, _I, _I, ctypes.POINTER(ShrinkInfo)]
+    _LL = ctypes.POINTER(ctypes.c_longlong)
+    dll.mrb_als_rank_agreement.restype = c_int
+    dll.mrb_als_rank_agreement.argtypes = [_I, c_int, _I, _I, _D, _D, _D, c_int, _D, c_int, c_int,
+                                           _LL, _LL, _I, ctypes.POINTER(ctypes.c_float)]
     dll.mrb_trim_memory.restype = None
     dll.mrb_trim_memory.argtypes = []
     dll.mrb_kernel_launches.restype = ctypes.c_longlong

@@ -88,10 +88,14 @@ __device__ __forceinline__ int work_index(int w, int n_work, int mode) {
 __device__ double g_zero_row[64];   // zero-initialised: the factor row of a padding rating
 
 template <int M8, bool USER, int EPI>
-#ifndef GRAM_MIN_CTAS
-#define GRAM_MIN_CTAS 1
-#endif
+// (no minimum-CTAs argument: naming even the default "1" changes ptxas' schedule of the movie-side
+// kernel -- 4.47 instead of 3.73 ms per launch at C3, profiles/ab_tree_r02.log; forcing 3 CTAs per
+// SM (168 registers, 0.3-0.9 KB of spills) was measured as well: 10.2 / 13.2 ms per sweep vs 9.8)
+#ifdef GRAM_MIN_CTAS
 __global__ void __launch_bounds__(gram_warps<USER>() * 32, GRAM_MIN_CTAS)
+#else
+__global__ void __launch_bounds__(gram_warps<USER>() * 32)
+#endif
 k_gram(const GramArgs A) {
     constexpr int ST = M8 * (M8 + 1) / 2;
     const int lane = threadIdx.x & 31;

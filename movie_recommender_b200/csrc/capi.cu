@@ -18,6 +18,7 @@
 #include "cosim.cuh"
 #include "prep.cuh"
 #include "peer.cuh"
+#include "evaluate.cuh"
 
 namespace mrb {
 static thread_local std::string g_last_error;
@@ -623,6 +624,26 @@ int mrb_cosine_topk(const double* factors, int num_items, int num_factors, int t
             info->total_ms = r.total_ms;
             info->fallback_rows = r.fallback_rows;
         }
+        return 0;
+    });
+}
+
+// ------------------------------------------------------------------ section 9: evaluation
+int mrb_als_rank_agreement(const int* user_ptr, int num_users, const int* entry_user_row,
+                           const int* entry_movie_row, const double* actual, const double* median,
+                           const double* user_factors, int num_user_rows,
+                           const double* item_factors, int num_items, int num_item_factors,
+                           long long* agree, long long* disagree, int* n_pred, float* kernel_ms) {
+    return guarded([&] {
+        MRB_REQUIRE(user_ptr != nullptr && agree != nullptr && disagree != nullptr && n_pred != nullptr,
+                    "mrb_als_rank_agreement: null argument");
+        MRB_REQUIRE(user_ptr[0] == 0, "mrb_als_rank_agreement: user_ptr[0] must be 0");
+        for (int u = 0; u < num_users; u++)
+            MRB_REQUIRE(user_ptr[u + 1] >= user_ptr[u], "mrb_als_rank_agreement: user_ptr must not decrease");
+        const float ms = als_rank_agreement(user_ptr, num_users, entry_user_row, entry_movie_row, actual,
+                                            median, user_factors, num_user_rows, item_factors, num_items,
+                                            num_item_factors, agree, disagree, n_pred);
+        if (kernel_ms) *kernel_ms = ms;
         return 0;
     });
 }

@@ -14,11 +14,11 @@ constexpr int PT = 256;  // threads per CTA of the streaming kernels
 
 // ---------------------------------------------------------------------------------- id check
 __global__ void __launch_bounds__(PT)
-k_check_range(const int* __restrict__ id, int n, int slots, int* __restrict__ bad) {
+k_check_range(const int* __restrict__ id, int n, int slots, int* __restrict__ bad, int lowest = 0) {
     const int i = blockIdx.x * PT + threadIdx.x;
     if (i < n) {
         const int v = id[i];
-        if (v < 0 || v >= slots) *bad = 1;
+        if (v < lowest || v >= slots) *bad = 1;
     }
 }
 
@@ -217,6 +217,15 @@ void check_id_range(const int* d_id, int n, int slots, const char* what, cudaStr
     DevBuf<int> bad(1);
     MRB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
     k_check_range<<<ceil_div(n, PT), PT, 0, s>>>(d_id, n, slots, bad.p); MRB_LAUNCHED(1);
+    MRB_CUDA(cudaGetLastError());
+    if (read_int(bad.p, s) != 0) throw Error(kErrArgument, std::string(what) + ": id out of range");
+}
+
+void check_id_range_allow_minus1(const int* d_id, int n, int limit, const char* what, cudaStream_t s) {
+    if (n <= 0) return;
+    DevBuf<int> bad(1);
+    MRB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+    k_check_range<<<ceil_div(n, PT), PT, 0, s>>>(d_id, n, limit, bad.p, -1); MRB_LAUNCHED(1);
     MRB_CUDA(cudaGetLastError());
     if (read_int(bad.p, s) != 0) throw Error(kErrArgument, std::string(what) + ": id out of range");
 }

@@ -23,6 +23,7 @@
 #include "similarity.cuh"
 
 #include <algorithm>
+#include <string>
 #include <vector>
 
 namespace mrb {
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(256)
 k_sim_rescore(const double* __restrict__ H, int n, int k, int topk, int q_lo, int q_hi,
               const int* __restrict__ cand_id, const double* __restrict__ cand_thr,
               const int* __restrict__ cand_cnt, int* __restrict__ ids_out,
-              double* __restrict__ scores_out, int* __restrict__ flags) {
+              double* __restrict__ scores_out, int* __restrict__ flags, double eps) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (q_lo + w >= q_hi) return;
@@ -293,6 +294,7 @@ k_sim_rescore(const double* __restrict__ H, int n, int k, int topk, int q_lo, in
 #pragma unroll
     for (int e = 0; e < 2; e++) {
         id[e] = cand_id[static_cast<size_t>(w) * SIM_C + lane + 32 * e];
+        if (id[e] == qrow) id[e] = -1;   // the tcgen05 candidate kernel lets the query itself ride along
         s[e] = id[e] >= 0 ? exact_score(a, H + static_cast<size_t>(id[e]) * k, k) : -1e300;
     }
     int rank[2] = {0, 0};
@@ -314,14 +316,16 @@ k_sim_rescore(const double* __restrict__ H, int n, int k, int topk, int q_lo, in
         const unsigned m = __ballot_sync(0xffffffffu, is_kth);
         if (m) kth = shfl_double(s[e], __ffs(m) - 1);
     }
-    const int cnt = cand_cnt[w];
-    for (int r = cnt + lane; r < topk; r += 32) {      // fewer candidates than topk: pad
+    const int cnt = cand_cnt[w];                        // list length (may include the query itself)
+    const int valid = __popc(__ballot_sync(0xffffffffu, id[0] >= 0)) + __popc(__ballot_sync(0xffffffffu, id[1] >= 0));
+    for (int r = valid + lane; r < topk; r += 32) {    // fewer candidates than topk: pad
         ids_out[static_cast<size_t>(w) * topk + r] = -1;
         scores_out[static_cast<size_t>(w) * topk + r] = 0.0;
     }
-    // Every dropped movie has approximate score <= cand_thr, hence exact score <= cand_thr + eps.
+    // Every dropped movie has approximate score <= cand_thr, hence exact score <= cand_thr + eps
+    // (eps = the candidate GEMM's error bound: 1e-12 for the fp64 path, SIM_TC_EPS for tf32).
     // It cannot belong to the top-k if the exact k-th score is clearly above that.
-    const bool certified = cnt < SIM_C || kth - cand_thr[w] > 1e-12;
+    const bool certified = cnt < SIM_C || kth - cand_thr[w] > eps;
     if (lane == 0) flags[w] = certified ? 0 : 1;
 }
 
@@ -416,6 +420,15 @@ SimResult cosine_topk(const double* M, int n, int k, int topk, int q_lo, int q_h
     MRB_CUDA(cudaEventRecord(e0, s));
     k_sim_normalize<<<ceil_div(n, 128), 128, 0, s>>>(d_M.p, n, k, kp, H.p, Hp.p);
     MRB_LAUNCHED(1);
+    // MRB_SIM_KERNEL=dmma selects the fp64 mma.sync candidate kernel (the round-1 path, kept as
+    // the A/B baseline); the default is the tcgen05 / TMA / TMEM kernel of similarity_tc.cu
+    const char* which = std::getenv("MRB_SIM_KERNEL");
+    const bool use_dmma = which != nullptr && std::string(which) == "dmma";
+    const double eps = use_dmma ? 1e-12 : SIM_TC_EPS;
+    if (!use_dmma) {
+        static_assert(SIM_C == 64, "similarity_tc.cu keeps 64 candidates per query as well");
+        cosine_candidates_tc(H.p, n, k, q_lo, q_hi, cand_id.p, cand_thr.p, cand_cnt.p, s);
+    } else
     switch (ks) {
         case 4: launch_candidates<4>(Hp.p, n, q_lo, q_hi, cand_id.p, cand_thr.p, cand_cnt.p, s); break;
         case 8: launch_candidates<8>(Hp.p, n, q_lo, q_hi, cand_id.p, cand_thr.p, cand_cnt.p, s); break;
@@ -424,7 +437,7 @@ SimResult cosine_topk(const double* M, int n, int k, int topk, int q_lo, int q_h
     }
     MRB_CUDA(cudaEventRecord(e1, s));
     k_sim_rescore<<<ceil_div(static_cast<long long>(nq) * 32, 256), 256, 0, s>>>(
-        H.p, n, k, topk, q_lo, q_hi, cand_id.p, cand_thr.p, cand_cnt.p, d_ids.p, d_scores.p, flags.p);
+        H.p, n, k, topk, q_lo, q_hi, cand_id.p, cand_thr.p, cand_cnt.p, d_ids.p, d_scores.p, flags.p, eps);
     MRB_LAUNCHED(1);
     MRB_CUDA(cudaGetLastError());
     std::vector<int> h_flags(nq);

@@ -5,7 +5,7 @@
 namespace mrb {
 
 struct SimResult {
-    float candidates_ms = 0;   // normalisation + DMMA GEMM fused with candidate selection
+    float candidates_ms = 0;   // normalisation + candidate GEMM fused with the selection
     float total_ms = 0;        // + exact re-score, final order, fallbacks (CUDA events)
     int fallback_rows = 0;     // queries recomputed exhaustively (certificate failed)
 };
@@ -14,5 +14,14 @@ struct SimResult {
 // padded when fewer than topk other movies exist.  topk <= 56, k <= 64.
 SimResult cosine_topk(const double* M, int n, int k, int topk, int q_lo, int q_hi, int* ids_out,
                       double* scores_out);
+
+// Phase A on the 5th-generation tensor cores (similarity_tc.cu): tcgen05.mma kind::tf32 with TMA
+// operands and TMEM accumulators, selection fused into the TMEM read-out.  d_H: device, n x k
+// normalised rows.  Candidate scores are within SIM_TC_EPS of the exact ones.
+constexpr double SIM_TC_EPS = 1.0e-3;
+void cosine_candidates_tc(const double* d_H, int n, int k, int q_lo, int q_hi, int* cand_id,
+                          double* cand_thr, int* cand_cnt, cudaStream_t s);
+int sim_tc_candidates();
+int sim_tc_padded_k();
 
 }  // namespace mrb

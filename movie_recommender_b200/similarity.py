@@ -16,6 +16,24 @@ from . import _lib
 _dll = _lib.dll
 
 
+def kernel_kind():
+    """Which candidate kernel ``factor_cosine_topk`` runs (``MRB_SIM_KERNEL=dmma`` selects the
+    fp64 mma.sync kernel the tcgen05 one replaced; kept for A/B runs)."""
+    import os
+    if os.environ.get("MRB_SIM_KERNEL") == "dmma":
+        return "fp64 DMMA (mma.sync m8n8k4)"
+    return "tcgen05.mma kind::tf32 (TMA operands, TMEM accumulators)"
+
+
+def padded_k(num_factors):
+    """Contraction length the candidate GEMM really executes."""
+    import os
+    if os.environ.get("MRB_SIM_KERNEL") == "dmma":
+        ks = (num_factors + 3) // 4
+        return 4 * (4 if ks <= 4 else 8 if ks <= 8 else 13 if ks <= 13 else 16)
+    return 8 * ((num_factors + 7) // 8)
+
+
 def factor_cosine_topk(item_factors, num_factors=None, topk=50, q_lo=0, q_hi=None):
     """Top-``topk`` most similar movies of every query movie ``q_lo <= q < q_hi``.
 

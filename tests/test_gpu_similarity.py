@@ -1,8 +1,12 @@
 """K5 factor-cosine top-k (config 4) against the CPU definition (oracle_cosine_topk; PARITY
 UNPINNED -- the reference has no factor-based similarity).  ids AND scores must be
-bit-exact: candidate selection runs on the fp64 tensor cores, the final scores are recomputed in
-the oracle's summation order, and a certificate triggers an exhaustive recomputation when
-near-ties at the boundary could not be excluded."""
+bit-exact: candidate selection runs on the tensor cores (default: tcgen05.mma kind::tf32 with TMA
+operands and TMEM accumulators, csrc/similarity_tc.cu; ``MRB_SIM_KERNEL=dmma``: the fp64 mma.sync
+kernel it replaced), the final scores are recomputed in the oracle's summation order, and a
+certificate -- widened by the candidate GEMM's error bound -- triggers an exhaustive recomputation
+when near-ties at the boundary could not be excluded.  Every test runs on both kernels."""
+import os
+
 import numpy as np
 import pytest
 
@@ -11,13 +15,27 @@ from conftest import bits_equal
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["tcgen05", "dmma"])
+def candidate_kernel(request):
+    old = os.environ.get("MRB_SIM_KERNEL")
+    if request.param == "dmma":
+        os.environ["MRB_SIM_KERNEL"] = "dmma"
+    else:
+        os.environ.pop("MRB_SIM_KERNEL", None)
+    yield request.param
+    if old is None:
+        os.environ.pop("MRB_SIM_KERNEL", None)
+    else:
+        os.environ["MRB_SIM_KERNEL"] = old
+
+
 def sim():
     from movie_recommender_b200 import similarity
     return similarity
 
 
 @pytest.mark.parametrize("n,k,topk", [(3000, 50, 50), (1000, 10, 20), (700, 33, 50), (257, 64, 56),
-                                      (64, 3, 50), (40, 50, 50)])
+                                      (64, 3, 50), (40, 50, 50), (6000, 50, 50), (129, 8, 5)])
 def test_topk_ids_and_scores_bitexact(require_gpu, oracle, n, k, topk):
     rng = np.random.default_rng(n + k)
     M = rng.standard_normal((n, k))
