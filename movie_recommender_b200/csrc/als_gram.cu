@@ -33,6 +33,7 @@
 #include "index_build.cuh"
 #include "native_cg.cuh"
 #include "gram_solve.cuh"
+#include "gram_wide.cuh"
 
 namespace mrb {
 
@@ -85,7 +86,7 @@ __device__ __forceinline__ int work_index(int w, int n_work, int mode) {
     return w;
 }
 
-__device__ double g_zero_row[64];   // zero-initialised: the factor row of a padding rating
+__device__ double g_zero_row[176];   // zero-initialised: the factor row of a padding rating
 
 template <int M8, bool USER, int EPI>
 // (no minimum-CTAs argument: naming even the default "1" changes ptxas' schedule of the movie-side
@@ -855,6 +856,51 @@ k_block_matvec(const double* __restrict__ G, const double* __restrict__ v, doubl
 
 }  // namespace
 
+namespace {
+// augmented order (unknowns + 1) -> is there a fused wide instantiation for its tile count?
+bool wide_fused_supported(int order) {
+    const int m8 = (order + 7) / 8;
+    return m8 == 9 || m8 == 13 || m8 == 17;
+}
+
+template <int M8, bool USER>
+void launch_wide_t(const GramArgs& a, int sms, cudaStream_t s) {
+    auto kern = k_gram_wide<M8, USER>;
+    const int smem = static_cast<int>(sizeof(WideSmem<M8>));
+    static std::atomic<int> per_sm_cached{0};
+    int per_sm = per_sm_cached.load(std::memory_order_relaxed);
+    if (per_sm == 0) {
+        MRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WIDE_WARPS * 32, smem));
+        MRB_REQUIRE(per_sm >= 1, "wide gram kernel does not fit on an SM");
+        per_sm_cached.store(per_sm, std::memory_order_relaxed);
+    }
+    const double* zero_row = nullptr;
+    MRB_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(const_cast<double**>(&zero_row)), g_zero_row));
+    const int grid = std::max(1, std::min(sms * per_sm, a.n_work));
+    kern<<<grid, WIDE_WARPS * 32, smem, s>>>(a, zero_row);
+    MRB_LAUNCHED(1);
+    MRB_CUDA(cudaGetLastError());
+}
+
+void launch_wide(const GramArgs& a, bool user_side, int sms, cudaStream_t s) {
+    const int m8 = (a.n + 1 + 7) / 8;
+    if (user_side) {
+        switch (m8) {
+            case 9: launch_wide_t<9, true>(a, sms, s); break;
+            case 13: launch_wide_t<13, true>(a, sms, s); break;
+            default: launch_wide_t<17, true>(a, sms, s); break;
+        }
+    } else {
+        switch (m8) {
+            case 9: launch_wide_t<9, false>(a, sms, s); break;
+            case 13: launch_wide_t<13, false>(a, sms, s); break;
+            default: launch_wide_t<17, false>(a, sms, s); break;
+        }
+    }
+}
+}  // namespace
+
 struct AlsProblem::GramState {
     Side user, item;
     DevBuf<double> partials;
@@ -866,7 +912,7 @@ struct AlsProblem::GramState {
     int built_rank = -1, built_world = -1, built_partition = -1;
     int per_sm_block_u = 0, per_sm_block_i = 0;   // occupancy of k_gram_block on this device
     // wide ranks (k > 54): per-batch stored matrices of the block-Gram + shared-memory Cholesky path
-    bool wide = false;
+    bool wide = false, wide_fused = false;
     DevBuf<double> wG, wg, wcorner;
     int wide_batch = 0;
     // algorithm 3 (Gram block-CG): stored blocks and CG vectors, sized for the larger side
@@ -895,8 +941,13 @@ void AlsProblem::ensure_gram() {
     MRB_CUDA(cudaEventRecord(ev_prepared_, s_));
     prepared_recorded_ = true;
     g.wide = m8 > 7;
-    g.st_doubles = g.wide ? 1 : m8 * (m8 + 1) / 2 * 64;
-    const int slots = g.wide ? 1 : std::max(g.user.n_slots, g.item.n_slots);
+    // the fused wide kernel (gram_wide.cuh) needs an instantiation for BOTH sides' tile counts;
+    // MRB_WIDE_BLOCKS=1 keeps the general block-wise path (A/B runs)
+    const bool wide_fused = g.wide && wide_fused_supported(n_u + 1) && wide_fused_supported(n_u) &&
+                            std::getenv("MRB_WIDE_BLOCKS") == nullptr;
+    g.wide_fused = wide_fused;
+    g.st_doubles = g.wide && !wide_fused ? 1 : m8 * (m8 + 1) / 2 * 64;
+    const int slots = g.wide && !wide_fused ? 1 : std::max(g.user.n_slots, g.item.n_slots);
     g.partials.alloc(static_cast<size_t>(std::max(slots, 1)) * g.st_doubles);
     if (g.wide) {
         const size_t nn = static_cast<size_t>(n_u) * n_u;
@@ -918,8 +969,46 @@ void AlsProblem::ensure_gram() {
 void AlsProblem::launch_half(bool user_side, cudaStream_t stream, int epilogue) {
     GramState& g = *gram_;
     Side& sd = user_side ? g.user : g.item;
+    if (g.wide_fused && epilogue == EPI_SOLVE) {
+        // ---- wide ranks, fused: one CTA per owner, tiles through shared memory (gram_wide.cuh)
+        if (sd.n_work == 0) return;
+        MRB_CUDA(cudaMemsetAsync(g.counters.p, 0, sizeof(int) * g.counters.n, stream));
+        GramArgs a{};
+        a.work = sd.work.p;
+        a.n_work = sd.n_work;
+        a.work_counter = g.counters.p;
+        a.other_g = sd.other_g.p;
+        a.rating_g = sd.rating_g.p;
+        a.other_f = user_side ? itf_.p : uf_.p;
+        a.other_stride = user_side ? k_ : k_ + 1;
+        a.k = k_;
+        a.n = user_side ? k_ + 1 : k_;
+        a.x = user_side ? uf_.p : itf_.p;
+        a.partials = g.partials.p;
+        a.seg_done = g.counters.p + 1;
+        a.debug_skip_solve = std::getenv("MRB_DEBUG_SKIP_SOLVE") != nullptr
+                                 ? std::atoi(std::getenv("MRB_DEBUG_SKIP_SOLVE")) : 0;
+        a.n_peers = 0;
+        const std::vector<double*>& peers = user_side ? uf_peers_ : itf_peers_;
+        for (size_t j = 0; j < peers.size(); j++)
+            if (static_cast<int>(j) != rank_ && peers[j] != nullptr && a.n_peers < 8)
+                a.x_peers[a.n_peers++] = peers[j];
+        if (!user_side) {
+            MRB_CUDA(cudaMemsetAsync(g.sse_owner.p, 0, sizeof(double) * g.sse_owner.n, stream));
+            a.sse_out = g.sse_owner.p;
+        }
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        MRB_CUDA(cudaEventCreate(&e0));
+        gram_events_.push_back(e0);
+        MRB_CUDA(cudaEventCreate(&e1));
+        gram_events_.push_back(e1);
+        MRB_CUDA(cudaEventRecord(e0, stream));
+        launch_wide(a, user_side, g.sms, stream);
+        MRB_CUDA(cudaEventRecord(e1, stream));
+        return;
+    }
     if (g.wide) {
-        // ---- wide ranks: block Gram to HBM, then one shared-memory Cholesky per owner
+        // ---- wide ranks, general path: block Gram to HBM, then one shared-memory Cholesky per owner
         const int n = user_side ? k_ + 1 : k_;
         const int m8 = (n + 1 + 7) / 8;
         GramBlockArgs a{};

@@ -1,0 +1,388 @@
+// Wide ranks (k = 57 ... 159; config 5 has k = 128): the lower triangle of a k = 128 Gram matrix is
+// 153 tiles of 8x8 -- 306 accumulator registers per lane, more than one warp has.  One CTA of four
+// warps therefore owns an owner (a user / a movie):
+//
+//   accumulate  the tile ROWS are cut into four bands of (nearly) equal tile count, one per warp
+//               (M8 = 17: rows [0,8) [8,12) [12,15) [15,17) = 36 / 42 / 42 / 33 tiles); every warp
+//               walks the owner's ratings with the same gather as k_gram -- ids and ratings of 32
+//               grouped positions per coalesced batch, factor rows straight into mma fragments, one
+//               k-step ahead -- and issues its band's DMMAs (mma.sync m8n8k4 f64).  The rows are
+//               gathered once per warp (the three other warps hit L1), not once per 4x7 block as
+//               the block-wise path this replaces did.
+//   hand-over   the tiles go to shared memory in fragment order (lane-contiguous 16 bytes: conflict
+//               free both ways).  Owners with more than GRAM_SEG ratings are cut into segments
+//               handled by different CTAs; their partial tiles meet in HBM and the CTA that
+//               arrives last sums them in segment order (deterministic).
+//   factorise   blocked right-looking Cholesky on the shared-memory tiles, the same mathematics as
+//               gram_solve (correction form, pivots below 1e-12 of the original diagonal skipped):
+//               per tile column warp 0 factors the 8x8 diagonal tile in registers with an identity
+//               tile riding along (-> W = L_d^-T), the panel tiles become X W and every trailing
+//               tile gets T -= L L^T on the tensor cores, spread over the four warps; operands are
+//               C fragments read back from shared memory -- the even/odd column split makes them
+//               valid A / B fragments as they are.
+//   solve       warp 0: delta_t = W_t (y_t - sum L^T delta), one 8x8 product per tile row; the
+//               solved row goes to this GPU's replica and to every peer replica.
+#pragma once
+#include "gram_solve.cuh"
+
+namespace mrb {
+
+namespace {
+
+constexpr int WIDE_WARPS = 4;
+
+// first tile row of band w (w = 0..4) for M8 tile rows: the cut that minimises the largest band
+__host__ __device__ constexpr int wide_band(int m8, int w) {
+    int best0 = 1, best1 = 2, best2 = 3, best = 1 << 30;
+    for (int a = 1; a < m8; a++)
+        for (int b = a + 1; b < m8; b++)
+            for (int c = b + 1; c < m8; c++) {
+                const int t0 = a * (a + 1) / 2, t1 = b * (b + 1) / 2 - t0 - 0,
+                          t2 = c * (c + 1) / 2 - b * (b + 1) / 2, t3 = m8 * (m8 + 1) / 2 - c * (c + 1) / 2;
+                int mx = t0 > t1 ? t0 : t1;
+                mx = mx > t2 ? mx : t2;
+                mx = mx > t3 ? mx : t3;
+                if (mx < best) { best = mx; best0 = a; best1 = b; best2 = c; }
+            }
+    return w == 0 ? 0 : w == 1 ? best0 : w == 2 ? best1 : w == 3 ? best2 : m8;
+}
+
+template <int M8>
+struct WideSmem {
+    static constexpr int ST = M8 * (M8 + 1) / 2;
+    double S[ST * 64];        // lower-triangular tiles, fragment order: [tile][lane][2]
+    double Wc[M8 * 64];       // W = L_d^-T per tile column, C-fragment order
+    double Wt[M8 * 64];       // W^T per tile column, C-fragment order (= B operand of X W)
+    double x0[M8 * 8];        // the owner's current factors (0 beyond n)
+    double thr[M8 * 8];       // pivot thresholds: 1e-12 of the original diagonal
+    double gd[M8 * 8];        // terms of x0.(g + g')
+    double corner;            // sum b^2, later the residual corner
+    int ticket, last;         // scheduler broadcast
+};
+
+// element (i, j), i >= j, of the tile array
+__device__ __forceinline__ int wide_at(int i, int j) {
+    return TI(i >> 3, j >> 3) * 64 + (((i & 7) << 2) + ((j & 7) >> 1)) * 2 + (j & 1);
+}
+
+// The 8-pivot factorisation of one diagonal tile with an identity tile riding along (the pivot
+// loop of gram_solve restricted to the tiles D and W): on return D = L_d (lower part), W = L_d^-T.
+// npiv < 8 only in the last tile column (index n, the right-hand side, is not a pivot); *corner
+// receives element (npiv, npiv) before the scaling -- the residual corner -- on every lane.
+__device__ __forceinline__ void wide_factor_diag(double& d0, double& d1, double& w0, double& w1,
+                                                 double thr, int npiv, int lane, double* corner) {
+    const int p = lane >> 2, q = lane & 3;
+    double invd = 0;
+#pragma unroll 1
+    for (int cp = 0; cp < 4; cp++) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int c = 2 * cp + j;
+            if (c < npiv) {
+                const double dv = j ? d1 : d0;
+                const bool ok = dv > thr && thr > 1e-290;
+                const double r = shfl_double(ok ? fast_rsqrt(dv) : 0.0, c * 4 + cp);
+                if (p == c) invd = r;
+                if (c < 7) {
+                    const double inv_d = r * r;
+                    const double m0 = shfl_double(dv, (2 * q) * 4 + cp);
+                    const double m1 = shfl_double(dv, (2 * q + 1) * 4 + cp);
+                    const double f0 = q > cp ? m0 * inv_d : 0.0;
+                    const double f1 = (j == 0 ? q >= cp : q > cp) ? m1 * inv_d : 0.0;
+                    const double xrc = shfl_double(dv, p * 4 + cp);
+                    d0 = fma(-xrc, f0, d0);
+                    d1 = fma(-xrc, f1, d1);
+                    const double wrc = shfl_double(j ? w1 : w0, p * 4 + cp);
+                    w0 = fma(-wrc, f0, w0);
+                    w1 = fma(-wrc, f1, w1);
+                }
+            }
+        }
+    }
+    if (corner != nullptr) {
+        const int pr = npiv;   // 0..7
+        *corner = shfl_double((pr & 1) ? d1 : d0, pr * 4 + (pr >> 1));
+    }
+    const double r0 = shfl_double(invd, (2 * q) * 4), r1 = shfl_double(invd, (2 * q + 1) * 4);
+    d0 *= r0;
+    d1 *= r1;
+    w0 *= r0;
+    w1 *= r1;
+}
+
+// One warp's band of the accumulation: tile rows [R0, R1), all columns up to the diagonal.
+template <int M8, bool USER, int R0, int R1>
+__device__ __forceinline__ void wide_accumulate(const GramArgs& A, const WorkItem& wi, int lane,
+                                                double* __restrict__ out_tiles /* [tile][lane][2] */,
+                                                const double* zero_row) {
+    constexpr int T0 = R0 * (R0 + 1) / 2;
+    constexpr int NT = R1 * (R1 + 1) / 2 - T0;
+    const int q = lane & 3, p = lane >> 2;
+    const int k = A.k;
+    double acc[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; t++) { acc[t][0] = 0; acc[t][1] = 0; }
+    const int cnt = wi.end - wi.beg;
+    const int nsteps = (cnt + 3) >> 2;
+    int ids_cur = 0, ids_nxt = 0;
+    double rts_cur = 0, rts_nxt = 0;
+    if (lane < cnt) { ids_cur = A.other_g[wi.beg + lane]; rts_cur = A.rating_g[wi.beg + lane]; }
+    if (32 + lane < cnt) { ids_nxt = A.other_g[wi.beg + 32 + lane]; rts_nxt = A.rating_g[wi.beg + 32 + lane]; }
+    // fragments of k-step st: lane (p, q) holds element 8 t + p of rating 4 st + q's augmented row
+    auto fetch = [&](double (&f)[R1], int st, int batch_of_cur) {
+        const bool from_next = (st >> 3) != batch_of_cur;
+        const int src = ((st & 7) << 2) + q;
+        const int id = __shfl_sync(0xffffffffu, from_next ? ids_nxt : ids_cur, src);
+        const double rt = shfl_double(from_next ? rts_nxt : rts_cur, src);
+        const bool valid = (st << 2) + q < cnt;
+        const double* row = valid ? A.other_f + static_cast<size_t>(id) * A.other_stride : zero_row;
+#pragma unroll
+        for (int t = 0; t < R1; t++) {
+            const int j = 8 * t + p;
+            double v;
+            if (8 * t + 7 < k) v = row[j];                       // plain tiles (compile-time for k >= 8 t + 8)
+            else if (j < k) v = row[j];
+            else if (USER) v = !valid ? 0.0 : (j == k ? 1.0 : (j == k + 1 ? rt : 0.0));
+            else v = (valid && j == k) ? rt - row[k] : 0.0;      // b = rating - user bias (matrix.cpp:1029)
+            f[t] = v;
+        }
+    };
+    double fa[R1], fb[R1];
+    fetch(fa, 0, 0);
+    for (int step = 0; step < nsteps; step += 2) {
+        // ---- even step: uses fa, requests fb
+        if (step + 1 < nsteps) fetch(fb, step + 1, step >> 3);
+#pragma unroll
+        for (int ti = R0; ti < R1; ti++)
+#pragma unroll
+            for (int tj = 0; tj <= ti; tj++)
+                dmma884(acc[TI(ti, tj) - T0][0], acc[TI(ti, tj) - T0][1], fa[ti], fa[tj]);
+        if (step + 1 >= nsteps) break;
+        // entering the next batch of 32 ratings with step + 2
+        if (((step + 2) & 7) == 0) {
+            ids_cur = ids_nxt;
+            rts_cur = rts_nxt;
+            const int e = ((step + 2) << 2) + 32 + lane;
+            ids_nxt = 0;
+            rts_nxt = 0;
+            if (e < cnt) { ids_nxt = A.other_g[wi.beg + e]; rts_nxt = A.rating_g[wi.beg + e]; }
+        }
+        // ---- odd step: uses fb, requests fa
+        if (step + 2 < nsteps) fetch(fa, step + 2, (step + 2) >> 3);
+#pragma unroll
+        for (int ti = R0; ti < R1; ti++)
+#pragma unroll
+            for (int tj = 0; tj <= ti; tj++)
+                dmma884(acc[TI(ti, tj) - T0][0], acc[TI(ti, tj) - T0][1], fb[ti], fb[tj]);
+    }
+#pragma unroll
+    for (int t = 0; t < NT; t++)
+        *reinterpret_cast<double2*>(out_tiles + (static_cast<size_t>(T0 + t) * 32 + lane) * 2) =
+            make_double2(acc[t][0], acc[t][1]);
+}
+
+// Sum of the segments' partial tiles of one band, in segment order, into shared memory.
+template <int M8, int R0, int R1>
+__device__ __forceinline__ void wide_reduce_band(const double* __restrict__ partials, int nseg, int lane,
+                                                 double* __restrict__ S) {
+    constexpr int ST = M8 * (M8 + 1) / 2;
+    constexpr int T0 = R0 * (R0 + 1) / 2, T1 = R1 * (R1 + 1) / 2;
+    for (int t = T0; t < T1; t++) {
+        double2 a = make_double2(0.0, 0.0);
+        for (int s = 0; s < nseg; s++) {
+            const double2 v = __ldcg(reinterpret_cast<const double2*>(
+                partials + (static_cast<size_t>(s) * ST + t) * 64 + lane * 2));
+            a.x += v.x;
+            a.y += v.y;
+        }
+        *reinterpret_cast<double2*>(S + (static_cast<size_t>(t) * 32 + lane) * 2) = a;
+    }
+}
+
+template <int M8, bool USER>
+__global__ void __launch_bounds__(WIDE_WARPS * 32, 2)
+k_gram_wide(const GramArgs A, const double* __restrict__ zero_row) {
+    constexpr int ST = M8 * (M8 + 1) / 2;
+    constexpr int TN = M8 - 1;
+    constexpr int B0 = wide_band(M8, 0), B1 = wide_band(M8, 1), B2 = wide_band(M8, 2),
+                  B3 = wide_band(M8, 3), B4 = wide_band(M8, 4);
+    extern __shared__ __align__(16) unsigned char wide_smem_raw[];
+    WideSmem<M8>& sm = *reinterpret_cast<WideSmem<M8>*>(wide_smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = lane >> 2, q = lane & 3;
+    const int n = A.n;
+    const int pr = n & 7;          // fragment row / column of index n (the right-hand side) in tile TN
+
+    for (;;) {
+        __syncthreads();           // the previous owner's shared memory is no longer needed
+        if (threadIdx.x == 0) sm.ticket = atomicAdd(A.work_counter, 1);
+        __syncthreads();
+        const int w = sm.ticket;
+        if (w >= A.n_work) break;
+        const WorkItem wi = A.work[w];
+        const bool multi = wi.nseg > 1;
+        double* dst = multi ? A.partials + (static_cast<size_t>(wi.slot) + wi.seg) * (ST * 64) : sm.S;
+        switch (warp) {
+            case 0: wide_accumulate<M8, USER, B0, B1>(A, wi, lane, dst, zero_row); break;
+            case 1: wide_accumulate<M8, USER, B1, B2>(A, wi, lane, dst, zero_row); break;
+            case 2: wide_accumulate<M8, USER, B2, B3>(A, wi, lane, dst, zero_row); break;
+            default: wide_accumulate<M8, USER, B3, B4>(A, wi, lane, dst, zero_row); break;
+        }
+        if (multi) {
+            // ordered reduction of the segments by the CTA that arrives last
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) sm.last = atomicAdd(A.seg_done + wi.multi, 1) == wi.nseg - 1;
+            __syncthreads();
+            if (!sm.last) continue;
+            __threadfence();
+            const double* src = A.partials + static_cast<size_t>(wi.slot) * (ST * 64);
+            switch (warp) {
+                case 0: wide_reduce_band<M8, B0, B1>(src, wi.nseg, lane, sm.S); break;
+                case 1: wide_reduce_band<M8, B1, B2>(src, wi.nseg, lane, sm.S); break;
+                case 2: wide_reduce_band<M8, B2, B3>(src, wi.nseg, lane, sm.S); break;
+                default: wide_reduce_band<M8, B3, B4>(src, wi.nseg, lane, sm.S); break;
+            }
+        }
+        if (A.debug_skip_solve & 1) continue;     // measurement only: time the accumulation alone
+        double* xo = A.x + static_cast<size_t>(wi.owner) * n;
+        for (int c = threadIdx.x; c < M8 * 8; c += blockDim.x) sm.x0[c] = c < n ? xo[c] : 0.0;
+        __syncthreads();
+
+        // ---- correction form: rhs' = g - G x0, thresholds from the original diagonal, and the
+        // terms of x0.(g + g') (residual bookkeeping); one thread per unknown.  Row n (the
+        // right-hand side) is read and written only by its own column's thread; every other read
+        // is of rows < n.
+        for (int c = threadIdx.x; c < M8 * 8; c += blockDim.x) {
+            if (c < n) {
+                const double g0 = sm.S[wide_at(n, c)];
+                double r = g0;
+                for (int i = 0; i < n; i++)
+                    r -= (i >= c ? sm.S[wide_at(i, c)] : sm.S[wide_at(c, i)]) * sm.x0[i];
+                sm.thr[c] = 1e-12 * sm.S[wide_at(c, c)];
+                sm.gd[c] = sm.x0[c] * (g0 + r);
+                sm.S[wide_at(n, c)] = r;
+            } else {
+                sm.thr[c] = 0.0;
+                sm.gd[c] = 0.0;
+            }
+        }
+        __syncthreads();
+
+        // ---- blocked Cholesky over the tile columns
+        for (int tk = 0; tk < M8; tk++) {
+            const int npiv = tk < TN ? 8 : pr;
+            if (warp == 0) {
+                double* D = sm.S + (static_cast<size_t>(TI(tk, tk)) * 32 + lane) * 2;
+                double d0 = D[0], d1 = D[1];
+                double w0 = p == 2 * q ? 1.0 : 0.0, w1 = p == 2 * q + 1 ? 1.0 : 0.0;
+                double corner = 0;
+                wide_factor_diag(d0, d1, w0, w1, sm.thr[8 * tk + p], npiv, lane, tk == TN ? &corner : nullptr);
+                D[0] = d0;
+                D[1] = d1;
+                sm.Wc[(tk * 32 + lane) * 2] = w0;
+                sm.Wc[(tk * 32 + lane) * 2 + 1] = w1;
+                // W^T as a C fragment: slot s of lane (p, q) = W[2q + s][p]
+#pragma unroll
+                for (int sl = 0; sl < 2; sl++) {
+                    const int src = (2 * q + sl) * 4 + (p >> 1);
+                    const double v0 = shfl_double(w0, src), v1 = shfl_double(w1, src);
+                    sm.Wt[(tk * 32 + lane) * 2 + sl] = (p & 1) ? v1 : v0;
+                }
+                if (tk == TN && lane == 0) sm.corner = corner;
+            }
+            __syncthreads();
+            if (tk == TN) break;
+            // panel: L(ti,tk) = X(ti,tk) W, tiles dealt over the warps
+            {
+                const double b0 = sm.Wt[(tk * 32 + lane) * 2], b1 = sm.Wt[(tk * 32 + lane) * 2 + 1];
+                for (int ti = tk + 1 + warp; ti < M8; ti += WIDE_WARPS) {
+                    double* X = sm.S + (static_cast<size_t>(TI(ti, tk)) * 32 + lane) * 2;
+                    const double2 x = *reinterpret_cast<const double2*>(X);
+                    double c0 = 0.0, c1 = 0.0;
+                    dmma884(c0, c1, x.x, b0);
+                    dmma884(c0, c1, x.y, b1);
+                    *reinterpret_cast<double2*>(X) = make_double2(c0, c1);
+                }
+            }
+            __syncthreads();
+            // trailing update: T(ti,tj) -= L(ti,tk) L(tj,tk)^T for tk < tj <= ti, dealt over the warps
+            {
+                const int m = M8 - 1 - tk;
+                const int total = m * (m + 1) / 2;
+                for (int e = warp; e < total; e += WIDE_WARPS) {
+                    // e -> (a, b), b <= a, row-major lower triangle of an m x m tile matrix
+                    int a = static_cast<int>((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+                    while ((a + 1) * (a + 2) / 2 <= e) a++;
+                    while (a * (a + 1) / 2 > e) a--;
+                    const int b = e - a * (a + 1) / 2;
+                    const int ti = tk + 1 + a, tj = tk + 1 + b;
+                    const double2 li = *reinterpret_cast<const double2*>(sm.S + (static_cast<size_t>(TI(ti, tk)) * 32 + lane) * 2);
+                    const double2 lj = *reinterpret_cast<const double2*>(sm.S + (static_cast<size_t>(TI(tj, tk)) * 32 + lane) * 2);
+                    double* T = sm.S + (static_cast<size_t>(TI(ti, tj)) * 32 + lane) * 2;
+                    double2 t = *reinterpret_cast<const double2*>(T);
+                    dmma884(t.x, t.y, -li.x, lj.x);     // even columns of the panel
+                    dmma884(t.x, t.y, -li.y, lj.y);     // odd columns
+                    *reinterpret_cast<double2*>(T) = t;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- residual and back substitution (warp 0); row n of the factor is y = L^-1 g'
+        if (warp == 0) {
+            if (A.sse_out != nullptr && lane == 0) {
+                double gdot = 0;
+                for (int c = 0; c < n; c++) gdot += sm.gd[c];
+                A.sse_out[wi.owner] = sm.corner - gdot;
+            }
+            double part[M8][2];
+#pragma unroll
+            for (int t = 0; t < M8; t++) { part[t][0] = 0; part[t][1] = 0; }
+#pragma unroll 1
+            for (int tj = M8 - 1; tj >= 0; tj--) {
+                double yv[2];
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    // y[8 tj + 2q + s]: row pr of tile (TN, tj)
+                    yv[s] = sm.S[(static_cast<size_t>(TI(TN, tj)) * 32 + pr * 4 + q) * 2 + s];
+                }
+                // part[] is indexed dynamically in a rolled loop: read it through a static scan
+                double ps0 = 0, ps1 = 0;
+#pragma unroll
+                for (int t = 0; t < M8; t++)
+                    if (t == tj) { ps0 = part[t][0]; ps1 = part[t][1]; }
+                yv[0] -= xor_sum_p(ps0);
+                yv[1] -= xor_sum_p(ps1);
+                const double wc0 = sm.Wc[(tj * 32 + lane) * 2], wc1 = sm.Wc[(tj * 32 + lane) * 2 + 1];
+                const double dp = xor_sum_q(fma(wc0, yv[0], wc1 * yv[1]));     // delta[8 tj + p]
+#pragma unroll
+                for (int t2 = 0; t2 < M8; t2++)
+                    if (t2 < tj) {
+                        const double2 l = *reinterpret_cast<const double2*>(
+                            sm.S + (static_cast<size_t>(TI(tj, t2)) * 32 + lane) * 2);
+                        part[t2][0] = fma(l.x, dp, part[t2][0]);
+                        part[t2][1] = fma(l.y, dp, part[t2][1]);
+                    }
+                // x = x0 + delta for this tile row, column layout -> the lanes with p == 0 store
+                const double dl0 = shfl_double(dp, (2 * q) * 4), dl1 = shfl_double(dp, (2 * q + 1) * 4);
+                if (p == 0) {
+#pragma unroll
+                    for (int s = 0; s < 2; s++) {
+                        const int c = 8 * tj + 2 * q + s;
+                        if (c < n) {
+                            const double v = sm.x0[c] + (s ? dl1 : dl0);
+                            xo[c] = v;
+                            for (int j = 0; j < A.n_peers; j++)
+                                A.x_peers[j][static_cast<size_t>(wi.owner) * n + c] = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+}  // namespace mrb

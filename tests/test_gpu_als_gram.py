@@ -189,9 +189,12 @@ def test_gram_cg_rows_without_ratings_and_determinism(require_gpu, cpp_ls):
 
 
 # ------------------------------------------------------------------------------------------------
-# Wide ranks (k > 54; config 5 uses k = 128): block-wise Gram to HBM + shared-memory Cholesky.
+# Wide ranks (k > 54; config 5 uses k = 128).  Tile counts 9 / 13 / 17 (k = 64, 100, 128 ...) run
+# the fused kernel of csrc/gram_wide.cuh (one CTA per owner, tiles through shared memory, blocked
+# tensor-core Cholesky); every other wide rank (k = 55 here) runs the general block-wise path.
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("nu,ni,nnz,k", [(150, 120, 14000, 64), (300, 260, 70000, 128), (90, 80, 7000, 55)])
+@pytest.mark.parametrize("nu,ni,nnz,k", [(150, 120, 14000, 64), (300, 260, 70000, 128), (90, 80, 7000, 55),
+                                         (220, 200, 40000, 100)])
 def test_wide_rank_cholesky_matches_numpy_exact_als(require_gpu, cpp_ls, oracle, nu, ni, nnz, k):
     p = synth.als_problem(nu, ni, nnz, k, seed=k)
     args = (p["user_ids"], p["item_ids"], p["ratings"], k)
@@ -207,6 +210,48 @@ def test_wide_rank_cholesky_matches_numpy_exact_als(require_gpu, cpp_ls, oracle,
     # the SSE derived from the factorisation equals the oracle's evaluation
     rmse = oracle.rmse(*args, uf, itf)
     assert abs(np.sqrt(info.last_rr / len(u)) - rmse) < 1e-8
+
+
+def test_wide_rank_heavy_owners_are_split_and_summed_in_order(require_gpu, cpp_ls):
+    """Movies with far more than 2048 ratings: their Gram tiles are accumulated by several CTAs
+    and summed in segment order.  Result against NumPy half-sweeps, and bit-identical run to run."""
+    nu, ni, nnz, k = 5000, 30, 120000, 64           # ~4000 ratings per movie
+    p = synth.als_problem(nu, ni, nnz, k, seed=3)
+    args = (p["user_ids"], p["item_ids"], p["ratings"], k)
+    outs = []
+    for _ in range(2):
+        with cpp_ls.AlsProblem(*args, nu, ni) as prob:
+            prob.set_factors(p["user_factors0"], p["item_factors0"])
+            prob.run(4, -1e300, 1)
+            outs.append(prob.get_factors())
+    assert bits_equal(outs[0][0], outs[1][0]) and bits_equal(outs[0][1], outs[1][1])
+    uf, itf = outs[0]
+    ru, ri = numpy_half_sweeps(p, p["user_factors0"], p["item_factors0"], sweeps=1)
+    u, i = p["user_ids"], p["item_ids"]
+    pa = (uf.reshape(nu, k + 1)[u, :k] * itf.reshape(ni, k)[i]).sum(1) + uf.reshape(nu, k + 1)[u, k]
+    pb = (ru.reshape(nu, k + 1)[u, :k] * ri.reshape(ni, k)[i]).sum(1) + ru.reshape(nu, k + 1)[u, k]
+    assert np.max(np.abs(pa - pb)) < 1e-6
+
+
+def test_wide_rank_fused_and_blockwise_paths_agree(require_gpu, cpp_ls, monkeypatch):
+    """MRB_WIDE_BLOCKS=1 keeps the general block-wise path: same mathematics, different rounding."""
+    nu, ni, nnz, k = 260, 240, 60000, 128
+    p = synth.als_problem(nu, ni, nnz, k, seed=11)
+    args = (p["user_ids"], p["item_ids"], p["ratings"], k)
+    res = {}
+    for mode in ("fused", "blocks"):
+        if mode == "blocks":
+            monkeypatch.setenv("MRB_WIDE_BLOCKS", "1")
+        with cpp_ls.AlsProblem(*args, nu, ni) as prob:
+            prob.set_factors(p["user_factors0"], p["item_factors0"])
+            info = prob.run(4, -1e300, 2)
+            res[mode] = prob.get_factors() + (info.last_rr,)
+    u, i = p["user_ids"], p["item_ids"]
+
+    def pred(uf, itf):
+        return (uf.reshape(nu, k + 1)[u, :k] * itf.reshape(ni, k)[i]).sum(1) + uf.reshape(nu, k + 1)[u, k]
+    assert np.max(np.abs(pred(*res["fused"][:2]) - pred(*res["blocks"][:2]))) < 1e-7
+    assert abs(res["fused"][2] - res["blocks"][2]) <= 1e-8 * abs(res["blocks"][2])
 
 
 def test_wide_rank_gram_cg_first_sweep(require_gpu, cpp_ls, oracle):

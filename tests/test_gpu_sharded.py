@@ -20,9 +20,9 @@ from movie_recommender_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("partition", [0, 1])
-def test_two_emulated_ranks_match_single_gpu_bitwise(require_gpu, cpp_ls, partition):
-    nu, ni, nnz, k = 3000, 900, 150000, 20
+@pytest.mark.parametrize("partition,k", [(0, 20), (1, 20), (1, 64)])
+def test_two_emulated_ranks_match_single_gpu_bitwise(require_gpu, cpp_ls, partition, k):
+    nu, ni, nnz = (3000, 900, 150000) if k == 20 else (700, 300, 90000)   # k = 64: the fused wide kernel
     p = synth.als_problem(nu, ni, nnz, k, seed=77)
     args = (p["user_ids"], p["item_ids"], p["ratings"], k, nu, ni)
     single = cpp_ls.als(p["user_ids"], p["item_ids"], p["ratings"], k, nu, ni, -1e300, 3, 4,
