@@ -157,17 +157,27 @@ class AlsProblem:
     """
 
     def __init__(self, user_ids, item_ids, ratings, num_item_factors, num_users, num_items,
-                 coo_slice=None):
+                 coo_slice=None, total_ratings=None):
         """``coo_slice=(begin, end)``: multi-GPU creation -- this process uploads only ratings
         begin..end-1 of the (full-length) arrays; the index build is deferred until the peers
         have pushed theirs (``open_peer_group``, ``push_coo``, ``peer_barrier``,
-        ``build_index``; ``sharded.ShardedAls`` drives that sequence)."""
+        ``build_index``; ``sharded.ShardedAls`` drives that sequence).  With ``total_ratings``
+        the three arrays ARE the slice (length end - begin) of a problem of that many ratings:
+        no process ever holds the whole COO on the host."""
         self._user_ids = numpy.ascontiguousarray(user_ids, dtype=numpy.int32)
         self._item_ids = numpy.ascontiguousarray(item_ids, dtype=numpy.int32)
         self._ratings = numpy.ascontiguousarray(ratings, dtype=numpy.double)
         self.k, self.num_users, self.num_items = num_item_factors, num_users, num_items
+        self.num_ratings = len(self._ratings) if total_ratings is None else int(total_ratings)
         self._h = ctypes.c_void_p()
-        if coo_slice is None:
+        if total_ratings is not None:
+            b, e = int(coo_slice[0]), int(coo_slice[1])
+            if e - b != len(self._ratings):
+                raise ValueError("coo_slice does not match the length of the slice arrays")
+            _lib.check(_dll.mrb_als_create_slice(
+                _lib.ip(self._user_ids), _lib.ip(self._item_ids), _lib.dp(self._ratings), b, e - b,
+                self.num_ratings, num_item_factors, num_users, num_items, ctypes.byref(self._h)))
+        elif coo_slice is None:
             _lib.check(_dll.mrb_als_create(
                 _lib.ip(self._user_ids), _lib.ip(self._item_ids), len(self._ratings),
                 _lib.dp(self._ratings), num_item_factors, num_users, num_items,
@@ -310,16 +320,28 @@ class AlsProblem:
         _lib.check(_dll.mrb_als_peer_barrier(self._h, ctypes.c_void_p(stream or 0),
                                              1 if stream is None else 0))
 
-    def upload_factor_rows(self, user_factors, item_factors, u_lo, u_hi, i_lo, i_hi):
-        """Rows of FULL-size host arrays into every replica (own upload + NVLink pushes),
-        asynchronous: the arrays are kept referenced until the next download / get_factors."""
-        self._pending_factors = (user_factors, item_factors)
-        _lib.check(_dll.mrb_als_upload_factor_rows(self._h, _lib.dp(user_factors), _lib.dp(item_factors),
-                                                   u_lo, u_hi, i_lo, i_hi))
+    def _row_base(self, rows_array, first_row, width):
+        """Pointer a FULL-size array would have if ``rows_array`` were its rows from ``first_row``
+        on: the C side only ever touches the rows of the range it is given."""
+        if rows_array.dtype != numpy.double or not rows_array.flags.c_contiguous:
+            raise ValueError("factor rows must be contiguous float64")
+        return ctypes.cast(ctypes.c_void_p(rows_array.ctypes.data - first_row * width * 8), _lib._D)
 
-    def download_factor_rows(self, user_factors, item_factors, u_lo, u_hi, i_lo, i_hi, stream):
-        _lib.check(_dll.mrb_als_download_factor_rows(self._h, _lib.dp(user_factors), _lib.dp(item_factors),
-                                                     u_lo, u_hi, i_lo, i_hi, ctypes.c_void_p(stream)))
+    def upload_factor_rows(self, user_factors, item_factors, u_lo, u_hi, i_lo, i_hi, rows_only=False):
+        """Rows of FULL-size host arrays into every replica (own upload + NVLink pushes),
+        asynchronous: the arrays are kept referenced until the next download / get_factors.
+        ``rows_only``: the arrays hold just the rows of the two ranges."""
+        self._pending_factors = (user_factors, item_factors)
+        up = self._row_base(user_factors, u_lo, self.k + 1) if rows_only else _lib.dp(user_factors)
+        ip_ = self._row_base(item_factors, i_lo, self.k) if rows_only else _lib.dp(item_factors)
+        _lib.check(_dll.mrb_als_upload_factor_rows(self._h, up, ip_, u_lo, u_hi, i_lo, i_hi))
+
+    def download_factor_rows(self, user_factors, item_factors, u_lo, u_hi, i_lo, i_hi, stream,
+                             rows_only=False):
+        up = self._row_base(user_factors, u_lo, self.k + 1) if rows_only else _lib.dp(user_factors)
+        ip_ = self._row_base(item_factors, i_lo, self.k) if rows_only else _lib.dp(item_factors)
+        _lib.check(_dll.mrb_als_download_factor_rows(self._h, up, ip_, u_lo, u_hi, i_lo, i_hi,
+                                                     ctypes.c_void_p(stream)))
         self._pending_factors = None
 
     def set_shard_partition(self, rank, world, partition):

@@ -71,12 +71,9 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
     // The ids go first on the compute stream; the ratings (half of the bytes, not needed by
     // the grouping) follow on the copy stream while the ids are being checked and grouped.
     if (slice_len_ > 0) {
-        MRB_CUDA(cudaMemcpyAsync(user_ids_.p + slice_begin_, user_ids, sizeof(int) * slice_len_,
-                                 cudaMemcpyHostToDevice, s_));
-        MRB_CUDA(cudaMemcpyAsync(item_ids_.p + slice_begin_, item_ids, sizeof(int) * slice_len_,
-                                 cudaMemcpyHostToDevice, s_));
-        MRB_CUDA(cudaMemcpyAsync(ratings_.p + slice_begin_, ratings, sizeof(double) * slice_len_,
-                                 cudaMemcpyHostToDevice, s_copy_));
+        copy_h2d(user_ids_.p + slice_begin_, user_ids, sizeof(int) * slice_len_, s_);
+        copy_h2d(item_ids_.p + slice_begin_, item_ids, sizeof(int) * slice_len_, s_);
+        copy_h2d(ratings_.p + slice_begin_, ratings, sizeof(double) * slice_len_, s_copy_);
     }
     MRB_CUDA(cudaEventRecord(ev_ratings_, s_copy_));
     ratings_pending_ = true;
@@ -169,8 +166,8 @@ void AlsProblem::upload_factor_rows(const double* user_factors, const double* it
                 "als: factor row range outside the matrices");
     const size_t n = k_ + 1, uo = static_cast<size_t>(u_lo) * n, ub = static_cast<size_t>(u_hi - u_lo) * n;
     const size_t io = static_cast<size_t>(i_lo) * k_, ib = static_cast<size_t>(i_hi - i_lo) * k_;
-    if (ib) MRB_CUDA(cudaMemcpyAsync(itf_.p + io, item_factors + io, sizeof(double) * ib, cudaMemcpyHostToDevice, s_copy_));
-    if (ub) MRB_CUDA(cudaMemcpyAsync(uf_.p + uo, user_factors + uo, sizeof(double) * ub, cudaMemcpyHostToDevice, s_copy_));
+    if (ib) copy_h2d(itf_.p + io, item_factors + io, sizeof(double) * ib, s_copy_);
+    if (ub) copy_h2d(uf_.p + uo, user_factors + uo, sizeof(double) * ub, s_copy_);
     for (size_t r = 0; r < uf_peers_.size(); r++) {
         if (static_cast<int>(r) == rank_ || uf_peers_[r] == nullptr) continue;
         if (ib) MRB_CUDA(cudaMemcpyAsync(itf_peers_[r] + io, itf_.p + io, sizeof(double) * ib, cudaMemcpyDefault, s_copy_));
@@ -187,8 +184,8 @@ void AlsProblem::download_factor_rows(double* user_factors, double* item_factors
                 "als: factor row range outside the matrices");
     const size_t n = k_ + 1, uo = static_cast<size_t>(u_lo) * n, ub = static_cast<size_t>(u_hi - u_lo) * n;
     const size_t io = static_cast<size_t>(i_lo) * k_, ib = static_cast<size_t>(i_hi - i_lo) * k_;
-    if (ub) MRB_CUDA(cudaMemcpyAsync(user_factors + uo, uf_.p + uo, sizeof(double) * ub, cudaMemcpyDeviceToHost, after));
-    if (ib) MRB_CUDA(cudaMemcpyAsync(item_factors + io, itf_.p + io, sizeof(double) * ib, cudaMemcpyDeviceToHost, after));
+    if (ub) copy_d2h(user_factors + uo, uf_.p + uo, sizeof(double) * ub, after);
+    if (ib) copy_d2h(item_factors + io, itf_.p + io, sizeof(double) * ib, after);
     MRB_CUDA(cudaStreamSynchronize(after));
 }
 

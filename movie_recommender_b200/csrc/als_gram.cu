@@ -866,7 +866,7 @@ bool wide_fused_supported(int order) {
 template <int M8, bool USER>
 void launch_wide_t(const GramArgs& a, int sms, cudaStream_t s) {
     auto kern = k_gram_wide<M8, USER>;
-    const int smem = static_cast<int>(sizeof(WideSmem<M8>));
+    const int smem = static_cast<int>(sizeof(WideSmem<M8>) + sizeof(WideStage<M8>));
     static std::atomic<int> per_sm_cached{0};
     int per_sm = per_sm_cached.load(std::memory_order_relaxed);
     if (per_sm == 0) {
@@ -1232,9 +1232,9 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
     }
     wait_factors();
     // the solved user factors travel to the host while the item half-sweep runs
-    auto copy_user_factors_out = [&]() {
+    auto copy_user_factors_out = [&](bool record = false) {
         if (out_uf_ == nullptr) return;
-        MRB_CUDA(cudaEventRecord(ev_user_done_, s_));
+        if (record) MRB_CUDA(cudaEventRecord(ev_user_done_, s_));
         MRB_CUDA(cudaStreamWaitEvent(s_copy_, ev_user_done_, 0));
         uf_.download(out_uf_, uf_.n, s_copy_);
         MRB_CUDA(cudaEventRecord(ev_uf_copied_, s_copy_));
@@ -1245,8 +1245,11 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
         if (uf_copy_in_flight) MRB_CUDA(cudaStreamWaitEvent(s_, ev_uf_copied_, 0));
         if (algorithm == ALS_GRAM_CHOLESKY) {
             launch_half(true, s_, EPI_SOLVE);
-            copy_user_factors_out();
+            MRB_CUDA(cudaEventRecord(ev_user_done_, s_));
             launch_half(false, s_, EPI_SOLVE);
+            // after the movie half-sweep is enqueued: a download into pageable memory blocks the
+            // host, and the copy must still overlap that half-sweep
+            copy_user_factors_out();
             // rr := sum of squared training errors (the exact solve leaves no normal-equation
             // residual to monitor); same relative-decrease rule as matrix.cpp:871-875.
             rr = shard_sse(s_);
@@ -1255,7 +1258,7 @@ AlsRunInfo AlsProblem::run_gram(int algorithm, double min_r_decrease, int max_it
             // als(), matrix.cpp:818, 854-855) with global alpha/beta over all owners
             launch_half(true, s_, EPI_STORE);
             CgResult ur = block_cg_solve(g, uf_.p, nu_, k_ + 1, s_);
-            copy_user_factors_out();
+            copy_user_factors_out(true);
             launch_half(false, s_, EPI_STORE);
             CgResult ir = block_cg_solve(g, itf_.p, ni_, k_, s_);
             info.cg_iterations += ur.iterations + ir.iterations;

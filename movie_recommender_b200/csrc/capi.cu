@@ -51,6 +51,7 @@ static int solve_ls(int variant, int A_rows, int A_cols, const int* rowptr, cons
     MRB_REQUIRE(A_rows >= 0 && A_cols >= 0, "cg_least_squares: negative dimension");
     MRB_REQUIRE(b_length == A_rows, "cg_least_squares: len(b) != rows of A");
     MRB_REQUIRE(x_length == A_cols, "cg_least_squares: len(x) != columns of A");
+    MRB_REQUIRE(rowptr[0] == 0, "cg_least_squares: row pointers must start at 0");
     const int nnz = rowptr[A_rows];
     MRB_REQUIRE(nnz >= 0, "cg_least_squares: negative nnz");
     cudaStream_t s;
@@ -67,6 +68,7 @@ static int solve_ls(int variant, int A_rows, int A_cols, const int* rowptr, cons
         d_b.upload(b, A_rows, s);
         d_x.upload(x, A_cols, s);
     }
+    check_csr(d_rowptr.p, A_rows, d_col.p, nnz, A_cols, "cg_least_squares", s);
     std::unique_ptr<CsrFaithfulOp> op_holder;
     {
         PhaseTimer t("  stable transpose");
@@ -222,6 +224,7 @@ int mrb_csr_transpose(int rows, int cols, const int* rowptr, const int* colidx, 
         d_rowptr.upload(rowptr, static_cast<size_t>(rows) + 1, s);
         d_col.upload(colidx, nnz, s);
         d_vals.upload(vals, nnz, s);
+        check_csr(d_rowptr.p, rows, d_col.p, nnz, cols, "mrb_csr_transpose", s);
         csr_transpose(rows, cols, nnz, d_rowptr.p, d_col.p, d_vals.p, d_tptr.p, d_trow.p, d_tval.p, s);
         d_tptr.download(t_ptr, static_cast<size_t>(cols) + 1, s);
         d_trow.download(t_row, nnz, s);
@@ -592,6 +595,19 @@ int mrb_cosim_create(int num_movies, int num_users, const int* m_ptr, const int*
                      const int* genre_cnt, mrb_cosim** out) {
     return guarded([&] {
         MRB_REQUIRE(out != nullptr, "mrb_cosim_create: null out");
+        MRB_REQUIRE(num_movies >= 0 && num_users >= 0 && m_ptr != nullptr && u_ptr != nullptr,
+                    "mrb_cosim_create: bad sizes");
+        // both CSR views are host arrays: validate them here, before anything reaches the device
+        auto check_view = [](const int* ptr, int rows, const int* idx, int limit, const char* what) {
+            MRB_REQUIRE(ptr[0] == 0, std::string(what) + ": pointers must start at 0");
+            for (int r = 0; r < rows; r++)
+                MRB_REQUIRE(ptr[r + 1] >= ptr[r], std::string(what) + ": pointers must not decrease");
+            bool ok = true;
+            for (int e = 0; e < ptr[rows]; e++) ok &= idx[e] >= 0 && idx[e] < limit;
+            MRB_REQUIRE(ok, std::string(what) + ": index out of range");
+        };
+        check_view(m_ptr, num_movies, m_user, num_users, "mrb_cosim_create (by movie)");
+        check_view(u_ptr, num_users, u_movie, num_movies, "mrb_cosim_create (by user)");
         *out = new mrb_cosim(num_movies, num_users, m_ptr, m_user, m_rq, u_ptr, u_movie, u_rq,
                              genre_mask, genre_cnt);
         return 0;

@@ -56,6 +56,14 @@ void* arena_alloc(size_t bytes);
 void arena_free(void* p);
 void arena_trim();
 
+// Host <-> device copies that do not collapse on PAGEABLE host memory (hostcopy.cu): large
+// pageable buffers are staged through page-locked chunks by a few host threads; page-locked
+// buffers and small copies are plain cudaMemcpyAsync on `s`.  A staged upload returns when the
+// source may be reused and is ordered after the work already enqueued on `s`; a staged download
+// returns when the data is in the destination.
+void copy_h2d(void* dev, const void* host, size_t bytes, cudaStream_t s);
+void copy_d2h(void* host, const void* dev, size_t bytes, cudaStream_t s);
+
 // RAII device allocation.
 template <typename T>
 struct DevBuf {
@@ -82,10 +90,10 @@ struct DevBuf {
         n = 0;
     }
     void upload(const T* host, size_t count, cudaStream_t s) {
-        if (count) MRB_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        if (count) copy_h2d(p, host, count * sizeof(T), s);
     }
     void download(T* host, size_t count, cudaStream_t s) const {
-        if (count) MRB_CUDA(cudaMemcpyAsync(host, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+        if (count) copy_d2h(host, p, count * sizeof(T), s);
     }
 };
 

@@ -3,23 +3,25 @@
 // warps therefore owns an owner (a user / a movie):
 //
 //   accumulate  the tile ROWS are cut into four bands of (nearly) equal tile count, one per warp
-//               (M8 = 17: rows [0,8) [8,12) [12,15) [15,17) = 36 / 42 / 42 / 33 tiles); every warp
-//               walks the owner's ratings with the same gather as k_gram -- ids and ratings of 32
-//               grouped positions per coalesced batch, factor rows straight into mma fragments, one
-//               k-step ahead -- and issues its band's DMMAs (mma.sync m8n8k4 f64).  The rows are
-//               gathered once per warp (the three other warps hit L1), not once per 4x7 block as
-//               the block-wise path this replaces did.
+//               (M8 = 17: rows [0,8) [8,12) [12,15) [15,17) = 36 / 42 / 42 / 33 tiles).  The four
+//               warps walk the owner's ratings together: per k-step (4 ratings) warp w copies
+//               rating w's factor row into a shared-memory ring (cp.async, 3 k-steps in flight, one
+//               barrier per k-step), every warp reads its band's mma fragments from there
+//               (conflict free: the padded row length is 8 mod 16 doubles) and issues its DMMAs
+//               (mma.sync m8n8k4 f64).  The rows cross L2 -> SM once per CTA, not once per warp or
+//               once per 4x7 block as in the block-wise path this replaces.
 //   hand-over   the tiles go to shared memory in fragment order (lane-contiguous 16 bytes: conflict
 //               free both ways).  Owners with more than GRAM_SEG ratings are cut into segments
 //               handled by different CTAs; their partial tiles meet in HBM and the CTA that
 //               arrives last sums them in segment order (deterministic).
-//   factorise   blocked right-looking Cholesky on the shared-memory tiles, the same mathematics as
+//   factorise   blocked LEFT-looking Cholesky on the shared-memory tiles, the same mathematics as
 //               gram_solve (correction form, pivots below 1e-12 of the original diagonal skipped):
-//               per tile column warp 0 factors the 8x8 diagonal tile in registers with an identity
-//               tile riding along (-> W = L_d^-T), the panel tiles become X W and every trailing
-//               tile gets T -= L L^T on the tensor cores, spread over the four warps; operands are
-//               C fragments read back from shared memory -- the even/odd column split makes them
-//               valid A / B fragments as they are.
+//               per tile column every warp brings its tiles up to date in registers against the
+//               finished columns (T -= L L^T on the tensor cores; the operands are the stored C
+//               fragments -- the even/odd column split makes them valid A / B fragments as they
+//               are), warp 0 factors the 8x8 diagonal tile with an identity tile riding along
+//               (-> W = L_d^-T) meanwhile, then the panel tiles become X W.  Every tile is written
+//               once; two barriers per tile column.
 //   solve       warp 0: delta_t = W_t (y_t - sum L^T delta), one 8x8 product per tile row; the
 //               solved row goes to this GPU's replica and to every peer replica.
 #pragma once
@@ -110,71 +112,102 @@ __device__ __forceinline__ void wide_factor_diag(double& d0, double& d1, double&
     w1 *= r1;
 }
 
-// One warp's band of the accumulation: tile rows [R0, R1), all columns up to the diagonal.
+constexpr int WIDE_STAGES = 3;     // k-steps of gathered rows in flight in shared memory
+
+template <int M8>
+struct WideStage {
+    double row[WIDE_STAGES][4][M8 * 8];   // 4 ratings per k-step; row length 8 (mod 16) doubles: conflict free
+};
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One warp's band of the accumulation: tile rows [R0, R1), all columns up to the diagonal.  The
+// four warps of the CTA walk the owner's ratings TOGETHER: warp w copies the factor row of rating
+// 4 st + w of k-step st into shared memory (cp.async, WIDE_STAGES k-steps ahead, one barrier per
+// k-step), and every warp reads the fragments of its band from there -- the rows cross L2 -> SM
+// once per CTA instead of once per warp.
 template <int M8, bool USER, int R0, int R1>
-__device__ __forceinline__ void wide_accumulate(const GramArgs& A, const WorkItem& wi, int lane,
-                                                double* __restrict__ out_tiles /* [tile][lane][2] */,
+__device__ __forceinline__ void wide_accumulate(const GramArgs& A, const WorkItem& wi, int warp, int lane,
+                                                WideStage<M8>& stg, double* __restrict__ out_tiles,
                                                 const double* zero_row) {
     constexpr int T0 = R0 * (R0 + 1) / 2;
     constexpr int NT = R1 * (R1 + 1) / 2 - T0;
     const int q = lane & 3, p = lane >> 2;
     const int k = A.k;
+    const int row_len = USER ? k : k + 1;          // doubles per gathered factor row
     double acc[NT][2];
 #pragma unroll
     for (int t = 0; t < NT; t++) { acc[t][0] = 0; acc[t][1] = 0; }
     const int cnt = wi.end - wi.beg;
     const int nsteps = (cnt + 3) >> 2;
+    // ids / ratings of 32 grouped positions per coalesced batch, two batches in registers
     int ids_cur = 0, ids_nxt = 0;
     double rts_cur = 0, rts_nxt = 0;
     if (lane < cnt) { ids_cur = A.other_g[wi.beg + lane]; rts_cur = A.rating_g[wi.beg + lane]; }
     if (32 + lane < cnt) { ids_nxt = A.other_g[wi.beg + 32 + lane]; rts_nxt = A.rating_g[wi.beg + 32 + lane]; }
-    // fragments of k-step st: lane (p, q) holds element 8 t + p of rating 4 st + q's augmented row
-    auto fetch = [&](double (&f)[R1], int st, int batch_of_cur) {
-        const bool from_next = (st >> 3) != batch_of_cur;
-        const int src = ((st & 7) << 2) + q;
-        const int id = __shfl_sync(0xffffffffu, from_next ? ids_nxt : ids_cur, src);
-        const double rt = shfl_double(from_next ? rts_nxt : rts_cur, src);
-        const bool valid = (st << 2) + q < cnt;
-        const double* row = valid ? A.other_f + static_cast<size_t>(id) * A.other_stride : zero_row;
-#pragma unroll
-        for (int t = 0; t < R1; t++) {
-            const int j = 8 * t + p;
-            double v;
-            if (8 * t + 7 < k) v = row[j];                       // plain tiles (compile-time for k >= 8 t + 8)
-            else if (j < k) v = row[j];
-            else if (USER) v = !valid ? 0.0 : (j == k ? 1.0 : (j == k + 1 ? rt : 0.0));
-            else v = (valid && j == k) ? rt - row[k] : 0.0;      // b = rating - user bias (matrix.cpp:1029)
-            f[t] = v;
+    int batch_of_cur = 0;                           // ids_cur holds batch batch_of_cur, ids_nxt the next one
+    // request k-step st: this warp copies rating 4 st + warp's row
+    auto request = [&](int st) {
+        if (st < nsteps) {
+            const bool from_next = (st >> 3) != batch_of_cur;
+            const int src = ((st & 7) << 2) + warp;
+            const int id = __shfl_sync(0xffffffffu, from_next ? ids_nxt : ids_cur, src);
+            const bool valid = (st << 2) + warp < cnt;
+            const double* row = valid ? A.other_f + static_cast<size_t>(id) * A.other_stride : zero_row;
+            double* dstrow = stg.row[st % WIDE_STAGES][warp];
+            for (int e = lane; e < row_len; e += 32) cp_async8(dstrow + e, row + e);
         }
+        cp_async_commit_group();                    // (possibly empty: keeps the group count in step)
     };
-    double fa[R1], fb[R1];
-    fetch(fa, 0, 0);
-    for (int step = 0; step < nsteps; step += 2) {
-        // ---- even step: uses fa, requests fb
-        if (step + 1 < nsteps) fetch(fb, step + 1, step >> 3);
+    // zero the tail of every staged row once (elements row_len .. 8 M8 - 1 are never copied)
+    for (int sidx = 0; sidx < WIDE_STAGES; sidx++)
+        for (int e = row_len + lane; e < M8 * 8; e += 32) stg.row[sidx][warp][e] = 0.0;
 #pragma unroll
-        for (int ti = R0; ti < R1; ti++)
-#pragma unroll
-            for (int tj = 0; tj <= ti; tj++)
-                dmma884(acc[TI(ti, tj) - T0][0], acc[TI(ti, tj) - T0][1], fa[ti], fa[tj]);
-        if (step + 1 >= nsteps) break;
-        // entering the next batch of 32 ratings with step + 2
-        if (((step + 2) & 7) == 0) {
+    for (int st = 0; st < WIDE_STAGES - 1; st++) request(st);
+    for (int step = 0; step < nsteps; step++) {
+        cp_async_wait_group<WIDE_STAGES - 2>();     // this thread's copies of k-step `step` have landed
+        __syncthreads();                            // ... everyone's have, and k-step step-1 is consumed
+        // the ratings of this k-step (for the special elements) before the batch registers move on
+        const bool fn = (step >> 3) != batch_of_cur;
+        const double rt = shfl_double(fn ? rts_nxt : rts_cur, ((step & 7) << 2) + q);
+        const bool valid = (step << 2) + q < cnt;
+        // refill the buffer k-step step-1 used; entering a new batch of 32 ratings first
+        const int nxt = step + WIDE_STAGES - 1;
+        if ((nxt >> 3) > batch_of_cur + 1) {
             ids_cur = ids_nxt;
             rts_cur = rts_nxt;
-            const int e = ((step + 2) << 2) + 32 + lane;
+            batch_of_cur++;
+            const int e = ((batch_of_cur + 1) << 5) + lane;
             ids_nxt = 0;
             rts_nxt = 0;
             if (e < cnt) { ids_nxt = A.other_g[wi.beg + e]; rts_nxt = A.rating_g[wi.beg + e]; }
         }
-        // ---- odd step: uses fb, requests fa
-        if (step + 2 < nsteps) fetch(fa, step + 2, (step + 2) >> 3);
+        request(nxt);
+        const double* srow = stg.row[step % WIDE_STAGES][q];
+        double f[R1];
+#pragma unroll
+        for (int t = 0; t < R1; t++) {
+            const int j = 8 * t + p;
+            double v = srow[j];                                   // raw factor (0 beyond the row)
+            if (8 * t + 7 >= k) {                                 // tiles that hold special elements
+                if (USER) v = j < k ? v : (!valid ? 0.0 : (j == k ? 1.0 : (j == k + 1 ? rt : 0.0)));
+                else v = j < k ? v : ((valid && j == k) ? rt - v : 0.0);   // rating - user bias (matrix.cpp:1029)
+            }
+            f[t] = v;
+        }
 #pragma unroll
         for (int ti = R0; ti < R1; ti++)
 #pragma unroll
             for (int tj = 0; tj <= ti; tj++)
-                dmma884(acc[TI(ti, tj) - T0][0], acc[TI(ti, tj) - T0][1], fb[ti], fb[tj]);
+                dmma884(acc[TI(ti, tj) - T0][0], acc[TI(ti, tj) - T0][1], f[ti], f[tj]);
     }
+    cp_async_wait_group<0>();
 #pragma unroll
     for (int t = 0; t < NT; t++)
         *reinterpret_cast<double2*>(out_tiles + (static_cast<size_t>(T0 + t) * 32 + lane) * 2) =
@@ -204,14 +237,17 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32, 2)
 k_gram_wide(const GramArgs A, const double* __restrict__ zero_row) {
     constexpr int ST = M8 * (M8 + 1) / 2;
     constexpr int TN = M8 - 1;
+    constexpr int NS = (M8 + WIDE_WARPS - 1) / WIDE_WARPS;      // tiles of one tile column per warp
     constexpr int B0 = wide_band(M8, 0), B1 = wide_band(M8, 1), B2 = wide_band(M8, 2),
                   B3 = wide_band(M8, 3), B4 = wide_band(M8, 4);
     extern __shared__ __align__(16) unsigned char wide_smem_raw[];
     WideSmem<M8>& sm = *reinterpret_cast<WideSmem<M8>*>(wide_smem_raw);
+    WideStage<M8>& stg = *reinterpret_cast<WideStage<M8>*>(wide_smem_raw + sizeof(WideSmem<M8>));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = lane >> 2, q = lane & 3;
     const int n = A.n;
     const int pr = n & 7;          // fragment row / column of index n (the right-hand side) in tile TN
+    auto tile = [&](int ti, int tj) { return sm.S + (static_cast<size_t>(TI(ti, tj)) * 32 + lane) * 2; };
 
     for (;;) {
         __syncthreads();           // the previous owner's shared memory is no longer needed
@@ -223,10 +259,10 @@ k_gram_wide(const GramArgs A, const double* __restrict__ zero_row) {
         const bool multi = wi.nseg > 1;
         double* dst = multi ? A.partials + (static_cast<size_t>(wi.slot) + wi.seg) * (ST * 64) : sm.S;
         switch (warp) {
-            case 0: wide_accumulate<M8, USER, B0, B1>(A, wi, lane, dst, zero_row); break;
-            case 1: wide_accumulate<M8, USER, B1, B2>(A, wi, lane, dst, zero_row); break;
-            case 2: wide_accumulate<M8, USER, B2, B3>(A, wi, lane, dst, zero_row); break;
-            default: wide_accumulate<M8, USER, B3, B4>(A, wi, lane, dst, zero_row); break;
+            case 0: wide_accumulate<M8, USER, B0, B1>(A, wi, warp, lane, stg, dst, zero_row); break;
+            case 1: wide_accumulate<M8, USER, B1, B2>(A, wi, warp, lane, stg, dst, zero_row); break;
+            case 2: wide_accumulate<M8, USER, B2, B3>(A, wi, warp, lane, stg, dst, zero_row); break;
+            default: wide_accumulate<M8, USER, B3, B4>(A, wi, warp, lane, stg, dst, zero_row); break;
         }
         if (multi) {
             // ordered reduction of the segments by the CTA that arrives last
@@ -249,16 +285,37 @@ k_gram_wide(const GramArgs A, const double* __restrict__ zero_row) {
         for (int c = threadIdx.x; c < M8 * 8; c += blockDim.x) sm.x0[c] = c < n ? xo[c] : 0.0;
         __syncthreads();
 
-        // ---- correction form: rhs' = g - G x0, thresholds from the original diagonal, and the
-        // terms of x0.(g + g') (residual bookkeeping); one thread per unknown.  Row n (the
-        // right-hand side) is read and written only by its own column's thread; every other read
-        // is of rows < n.
+        // ---- correction form: v = G x0 tile row by tile row (rows dealt over the warps; the row
+        // part from the tiles left of the diagonal, the column part from the tiles below it, as in
+        // gram_solve), then rhs' = g - v on row n, thresholds and the terms of x0.(g + g')
+        for (int ti = warp; ti < M8; ti += WIDE_WARPS) {
+            double rowsum = 0, col0 = 0, col1 = 0;
+            for (int tj = 0; tj <= ti; tj++) {
+                const double2 t = *reinterpret_cast<const double2*>(tile(ti, tj));
+                if (tj < ti) rowsum += t.x * sm.x0[8 * tj + 2 * q] + t.y * sm.x0[8 * tj + 2 * q + 1];
+                else { col0 += t.x * sm.x0[8 * ti + p]; col1 += t.y * sm.x0[8 * ti + p]; }   // diagonal tile: once
+            }
+            for (int tk = ti + 1; tk < M8; tk++) {
+                const double2 t = *reinterpret_cast<const double2*>(tile(tk, ti));
+                const double xr = sm.x0[8 * tk + p];
+                col0 += t.x * xr;
+                col1 += t.y * xr;
+            }
+            col0 = xor_sum_p(col0);
+            col1 = xor_sum_p(col1);
+            rowsum = xor_sum_q(rowsum);                       // indexed by p, replicated over q
+            const double v0 = col0 + shfl_double(rowsum, (2 * q) * 4);
+            const double v1 = col1 + shfl_double(rowsum, (2 * q + 1) * 4);
+            if (p == 0) {                                     // column layout: lanes (0, q) own columns 2q, 2q+1
+                sm.gd[8 * ti + 2 * q] = v0;                   // (gd doubles as the scratch for v)
+                sm.gd[8 * ti + 2 * q + 1] = v1;
+            }
+        }
+        __syncthreads();
         for (int c = threadIdx.x; c < M8 * 8; c += blockDim.x) {
             if (c < n) {
                 const double g0 = sm.S[wide_at(n, c)];
-                double r = g0;
-                for (int i = 0; i < n; i++)
-                    r -= (i >= c ? sm.S[wide_at(i, c)] : sm.S[wide_at(c, i)]) * sm.x0[i];
+                const double r = g0 - sm.gd[c];
                 sm.thr[c] = 1e-12 * sm.S[wide_at(c, c)];
                 sm.gd[c] = sm.x0[c] * (g0 + r);
                 sm.S[wide_at(n, c)] = r;
@@ -269,17 +326,38 @@ k_gram_wide(const GramArgs A, const double* __restrict__ zero_row) {
         }
         __syncthreads();
 
-        // ---- blocked Cholesky over the tile columns
+        // ---- blocked LEFT-LOOKING Cholesky over the tile columns: every tile is read as it was
+        // accumulated, brought up to date in registers against the finished columns to its left
+        // (T -= L(ti,j) L(tk,j)^T, operands straight from the stored C fragments: even columns in
+        // one mma, odd ones in the other), and written once, as L.  Warp 0 takes the diagonal tile
+        // and factors it while the other warps update their panel tiles.
         for (int tk = 0; tk < M8; tk++) {
             const int npiv = tk < TN ? 8 : pr;
+            double2 acc[NS];
+            // slot s of warp w: tile row ti = tk + w + 4 s (slot 0 of warp 0 is the diagonal tile)
+#pragma unroll
+            for (int sl = 0; sl < NS; sl++) {
+                const int ti = tk + warp + WIDE_WARPS * sl;
+                acc[sl] = ti < M8 ? *reinterpret_cast<const double2*>(tile(ti, tk)) : make_double2(0.0, 0.0);
+            }
+            for (int j = 0; j < tk; j++) {
+                const double2 lk = *reinterpret_cast<const double2*>(tile(tk, j));
+#pragma unroll
+                for (int sl = 0; sl < NS; sl++) {
+                    const int ti = tk + warp + WIDE_WARPS * sl;
+                    if (ti < M8) {                            // warp-uniform
+                        const double2 li = *reinterpret_cast<const double2*>(tile(ti, j));
+                        dmma884(acc[sl].x, acc[sl].y, -li.x, lk.x);
+                        dmma884(acc[sl].x, acc[sl].y, -li.y, lk.y);
+                    }
+                }
+            }
             if (warp == 0) {
-                double* D = sm.S + (static_cast<size_t>(TI(tk, tk)) * 32 + lane) * 2;
-                double d0 = D[0], d1 = D[1];
+                double d0 = acc[0].x, d1 = acc[0].y;
                 double w0 = p == 2 * q ? 1.0 : 0.0, w1 = p == 2 * q + 1 ? 1.0 : 0.0;
                 double corner = 0;
                 wide_factor_diag(d0, d1, w0, w1, sm.thr[8 * tk + p], npiv, lane, tk == TN ? &corner : nullptr);
-                D[0] = d0;
-                D[1] = d1;
+                *reinterpret_cast<double2*>(tile(tk, tk)) = make_double2(d0, d1);
                 sm.Wc[(tk * 32 + lane) * 2] = w0;
                 sm.Wc[(tk * 32 + lane) * 2 + 1] = w1;
                 // W^T as a C fragment: slot s of lane (p, q) = W[2q + s][p]
@@ -291,42 +369,22 @@ k_gram_wide(const GramArgs A, const double* __restrict__ zero_row) {
                 }
                 if (tk == TN && lane == 0) sm.corner = corner;
             }
-            __syncthreads();
+            __syncthreads();                                  // W^T of this column is published
             if (tk == TN) break;
-            // panel: L(ti,tk) = X(ti,tk) W, tiles dealt over the warps
             {
                 const double b0 = sm.Wt[(tk * 32 + lane) * 2], b1 = sm.Wt[(tk * 32 + lane) * 2 + 1];
-                for (int ti = tk + 1 + warp; ti < M8; ti += WIDE_WARPS) {
-                    double* X = sm.S + (static_cast<size_t>(TI(ti, tk)) * 32 + lane) * 2;
-                    const double2 x = *reinterpret_cast<const double2*>(X);
-                    double c0 = 0.0, c1 = 0.0;
-                    dmma884(c0, c1, x.x, b0);
-                    dmma884(c0, c1, x.y, b1);
-                    *reinterpret_cast<double2*>(X) = make_double2(c0, c1);
+#pragma unroll
+                for (int sl = 0; sl < NS; sl++) {
+                    const int ti = tk + warp + WIDE_WARPS * sl;
+                    if (ti > tk && ti < M8) {                 // panel: L(ti,tk) = X W
+                        double c0 = 0.0, c1 = 0.0;
+                        dmma884(c0, c1, acc[sl].x, b0);
+                        dmma884(c0, c1, acc[sl].y, b1);
+                        *reinterpret_cast<double2*>(tile(ti, tk)) = make_double2(c0, c1);
+                    }
                 }
             }
-            __syncthreads();
-            // trailing update: T(ti,tj) -= L(ti,tk) L(tj,tk)^T for tk < tj <= ti, dealt over the warps
-            {
-                const int m = M8 - 1 - tk;
-                const int total = m * (m + 1) / 2;
-                for (int e = warp; e < total; e += WIDE_WARPS) {
-                    // e -> (a, b), b <= a, row-major lower triangle of an m x m tile matrix
-                    int a = static_cast<int>((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-                    while ((a + 1) * (a + 2) / 2 <= e) a++;
-                    while (a * (a + 1) / 2 > e) a--;
-                    const int b = e - a * (a + 1) / 2;
-                    const int ti = tk + 1 + a, tj = tk + 1 + b;
-                    const double2 li = *reinterpret_cast<const double2*>(sm.S + (static_cast<size_t>(TI(ti, tk)) * 32 + lane) * 2);
-                    const double2 lj = *reinterpret_cast<const double2*>(sm.S + (static_cast<size_t>(TI(tj, tk)) * 32 + lane) * 2);
-                    double* T = sm.S + (static_cast<size_t>(TI(ti, tj)) * 32 + lane) * 2;
-                    double2 t = *reinterpret_cast<const double2*>(T);
-                    dmma884(t.x, t.y, -li.x, lj.x);     // even columns of the panel
-                    dmma884(t.x, t.y, -li.y, lj.y);     // odd columns
-                    *reinterpret_cast<double2*>(T) = t;
-                }
-            }
-            __syncthreads();
+            __syncthreads();                                  // column tk is final
         }
 
         // ---- residual and back substitution (warp 0); row n of the factor is y = L^-1 g'
@@ -339,31 +397,24 @@ k_gram_wide(const GramArgs A, const double* __restrict__ zero_row) {
             double part[M8][2];
 #pragma unroll
             for (int t = 0; t < M8; t++) { part[t][0] = 0; part[t][1] = 0; }
-#pragma unroll 1
+#pragma unroll
             for (int tj = M8 - 1; tj >= 0; tj--) {
-                double yv[2];
-#pragma unroll
-                for (int s = 0; s < 2; s++) {
-                    // y[8 tj + 2q + s]: row pr of tile (TN, tj)
-                    yv[s] = sm.S[(static_cast<size_t>(TI(TN, tj)) * 32 + pr * 4 + q) * 2 + s];
+                // y[8 tj + 2q + s]: row pr of tile (TN, tj)
+                const double2 y = *reinterpret_cast<const double2*>(
+                    sm.S + (static_cast<size_t>(TI(TN, tj)) * 32 + pr * 4 + q) * 2);
+                double yv0 = y.x, yv1 = y.y;
+                if (tj < M8 - 1) {
+                    yv0 -= xor_sum_p(part[tj][0]);
+                    yv1 -= xor_sum_p(part[tj][1]);
                 }
-                // part[] is indexed dynamically in a rolled loop: read it through a static scan
-                double ps0 = 0, ps1 = 0;
-#pragma unroll
-                for (int t = 0; t < M8; t++)
-                    if (t == tj) { ps0 = part[t][0]; ps1 = part[t][1]; }
-                yv[0] -= xor_sum_p(ps0);
-                yv[1] -= xor_sum_p(ps1);
                 const double wc0 = sm.Wc[(tj * 32 + lane) * 2], wc1 = sm.Wc[(tj * 32 + lane) * 2 + 1];
-                const double dp = xor_sum_q(fma(wc0, yv[0], wc1 * yv[1]));     // delta[8 tj + p]
+                const double dp = xor_sum_q(fma(wc0, yv0, wc1 * yv1));     // delta[8 tj + p]
 #pragma unroll
-                for (int t2 = 0; t2 < M8; t2++)
-                    if (t2 < tj) {
-                        const double2 l = *reinterpret_cast<const double2*>(
-                            sm.S + (static_cast<size_t>(TI(tj, t2)) * 32 + lane) * 2);
-                        part[t2][0] = fma(l.x, dp, part[t2][0]);
-                        part[t2][1] = fma(l.y, dp, part[t2][1]);
-                    }
+                for (int t2 = 0; t2 < tj; t2++) {
+                    const double2 l = *reinterpret_cast<const double2*>(tile(tj, t2));
+                    part[t2][0] = fma(l.x, dp, part[t2][0]);
+                    part[t2][1] = fma(l.y, dp, part[t2][1]);
+                }
                 // x = x0 + delta for this tile row, column layout -> the lanes with p == 0 store
                 const double dl0 = shfl_double(dp, (2 * q) * 4), dl1 = shfl_double(dp, (2 * q + 1) * 4);
                 if (p == 0) {

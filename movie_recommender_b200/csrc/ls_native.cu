@@ -10,6 +10,7 @@
 // All HBM streaming; algorithmic bytes per iteration (nnz_A = non-zeros):
 //   2*nnz_A*(8+4) + (rows+cols+2)*4 + rows*8 + nnz_A*8 + 7*cols*8.
 #include "ls_native.cuh"
+#include "prep.cuh"
 
 #include <cstdlib>
 #include <string>
@@ -197,6 +198,7 @@ k_csc_fold_group(const int* __restrict__ col_piece_ptr, const double* __restrict
 LsNativeResult solve_ls_native(int rows, int cols, const int* rowptr, const int* colidx,
                                const double* vals, const double* b, double* x,
                                double min_r_decrease, int max_iteration) {
+    MRB_REQUIRE(rowptr[0] == 0 && rowptr[rows] >= 0, "cg_least_squares: bad row pointers");
     const int nnz = rowptr[rows];
     cudaStream_t s;
     MRB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -208,6 +210,7 @@ LsNativeResult solve_ls_native(int rows, int cols, const int* rowptr, const int*
     d_vals.upload(vals, nnz, s);
     d_b.upload(b, rows, s);
     d_x.upload(x, cols, s);
+    check_csr(d_rowptr.p, rows, d_col.p, nnz, cols, "cg_least_squares", s);
 
     cudaEvent_t e0, e1, e2;
     MRB_CUDA(cudaEventCreate(&e0));

@@ -221,6 +221,29 @@ void check_id_range(const int* d_id, int n, int slots, const char* what, cudaStr
     if (read_int(bad.p, s) != 0) throw Error(kErrArgument, std::string(what) + ": id out of range");
 }
 
+namespace {
+__global__ void k_check_rowptr(const int* __restrict__ ptr, int rows, int* __restrict__ bad) {
+    const int i = blockIdx.x * PT + threadIdx.x;
+    if (i < rows && ptr[i + 1] < ptr[i]) *bad = 1;
+    if (i == 0 && ptr[0] != 0) *bad = 1;
+}
+}  // namespace
+
+// A CSR operator handed over by a caller: rowptr[0] == 0, rowptr non-decreasing, every column
+// index inside [0, cols).  One bad index would otherwise become an out-of-bounds device access
+// and a sticky context error for every later call of the process.
+void check_csr(const int* d_rowptr, int rows, const int* d_colidx, int nnz, int cols, const char* what,
+               cudaStream_t s) {
+    DevBuf<int> bad(1);
+    MRB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+    if (rows > 0) { k_check_rowptr<<<ceil_div(rows, PT), PT, 0, s>>>(d_rowptr, rows, bad.p); MRB_LAUNCHED(1); }
+    if (nnz > 0) { k_check_range<<<ceil_div(nnz, PT), PT, 0, s>>>(d_colidx, nnz, cols, bad.p); MRB_LAUNCHED(1); }
+    MRB_CUDA(cudaGetLastError());
+    if (read_int(bad.p, s) != 0)
+        throw Error(kErrArgument, std::string(what) + ": row pointers must start at 0 and not decrease, "
+                                                      "column indices must lie in [0, columns)");
+}
+
 void check_id_range_allow_minus1(const int* d_id, int n, int limit, const char* what, cudaStream_t s) {
     if (n <= 0) return;
     DevBuf<int> bad(1);

@@ -30,5 +30,8 @@ ShrinkCounts als_shrink(const int* d_user, const int* d_movie, const double* d_r
 
 // Throws kErrArgument if any id[i] is outside [0, slots).
 void check_id_range(const int* d_id, int n, int slots, const char* what, cudaStream_t s);
+// CSR sanity (rowptr[0] == 0, non-decreasing; colidx in [0, cols)): throws kErrArgument
+void check_csr(const int* d_rowptr, int rows, const int* d_colidx, int nnz, int cols, const char* what,
+               cudaStream_t s);
 
 }  // namespace mrb

@@ -329,6 +329,77 @@ k_sim_rescore(const double* __restrict__ H, int n, int k, int topk, int q_lo, in
     if (lane == 0) flags[w] = certified ? 0 : 1;
 }
 
+// The same for the two-pass tcgen05 path: up to 4 x 48 candidates per query (every column whose
+// approximate score reached the row's fixed threshold cand_thr, ~66 of them), 6 per lane.
+// Columns that were NOT collected have approximate score < cand_thr, hence exact score <
+// cand_thr + eps: the result is certified when the exact k-th score clears that.  A row whose
+// list overflowed (massive ties) is flagged for the exhaustive recomputation.
+__global__ void __launch_bounds__(256)
+k_sim_rescore_wide(const double* __restrict__ H, int n, int k, int topk, int q_lo, int q_hi,
+                   const int* __restrict__ cand_id, const double* __restrict__ cand_thr,
+                   const int* __restrict__ cand_cnt, int cap, int groups, int* __restrict__ ids_out,
+                   double* __restrict__ scores_out, int* __restrict__ flags, double eps) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q_lo + w >= q_hi) return;
+    const int qrow = q_lo + w;
+    const double* a = H + static_cast<size_t>(qrow) * k;
+    // `groups` lists of cap / groups slots each, with their own counts (one per column group of
+    // the collect pass); a list that overflowed sends the query to the exhaustive fallback
+    const int sub = cap / groups;
+    bool overflow = false;
+    for (int g = 0; g < groups; g++) overflow |= cand_cnt[static_cast<size_t>(w) * groups + g] > sub;
+    if (overflow) {
+        if (lane == 0) flags[w] = 1;
+        return;
+    }
+    constexpr int PER = 6;                 // cap <= 192
+    double s[PER];
+    int id[PER];
+#pragma unroll
+    for (int e = 0; e < PER; e++) {
+        const int slot = lane + 32 * e;
+        const int g = slot / sub, within = slot - g * sub;
+        id[e] = (slot < cap && within < cand_cnt[static_cast<size_t>(w) * groups + g])
+                    ? cand_id[static_cast<size_t>(w) * cap + slot] : -1;
+        if (id[e] == qrow) id[e] = -1;     // the query itself rides along in the candidate list
+        s[e] = id[e] >= 0 ? exact_score(a, H + static_cast<size_t>(id[e]) * k, k) : -1e300;
+    }
+    int rank[PER] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int g = 0; g < PER; g++) {
+        // broadcast the 32 candidates of register slot g one by one
+        const double sg = s[g];
+        const int ig = id[g];
+        if (__ballot_sync(0xffffffffu, ig >= 0) == 0) continue;
+        for (int f = 0; f < 32; f++) {
+            const double sf = shfl_double(sg, f);
+            const int idf = __shfl_sync(0xffffffffu, ig, f);
+            if (idf < 0) continue;
+#pragma unroll
+            for (int e = 0; e < PER; e++) rank[e] += precedes(sf, idf, s[e], id[e]) ? 1 : 0;
+        }
+    }
+    double kth = -1e300;
+    int valid = 0;
+#pragma unroll
+    for (int e = 0; e < PER; e++) {
+        if (id[e] >= 0 && rank[e] < topk) {
+            ids_out[static_cast<size_t>(w) * topk + rank[e]] = id[e];
+            scores_out[static_cast<size_t>(w) * topk + rank[e]] = s[e];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, id[e] >= 0 && rank[e] == topk - 1);
+        if (m) kth = shfl_double(s[e], __ffs(m) - 1);
+        valid += __popc(__ballot_sync(0xffffffffu, id[e] >= 0));
+    }
+    for (int r = valid + lane; r < topk; r += 32) {
+        ids_out[static_cast<size_t>(w) * topk + r] = -1;
+        scores_out[static_cast<size_t>(w) * topk + r] = 0.0;
+    }
+    const bool certified = kth - cand_thr[w] > eps;     // kth = -1e300 when fewer than topk candidates
+    if (lane == 0) flags[w] = certified ? 0 : 1;
+}
+
 // Exhaustive exact recomputation of one flagged query (rare): one CTA, top-k by repeated argmax.
 __global__ void __launch_bounds__(256)
 k_sim_exact_row(const double* __restrict__ H, int n, int k, int topk, int q_lo,
@@ -408,7 +479,18 @@ SimResult cosine_topk(const double* M, int n, int k, int topk, int q_lo, int q_h
     DevBuf<double> d_M(static_cast<size_t>(n) * k), H(static_cast<size_t>(n) * k),
         Hp(static_cast<size_t>(n) * kp + 16);
     d_M.upload(M, static_cast<size_t>(n) * k, s);
-    DevBuf<int> cand_id(static_cast<size_t>(nq) * SIM_C), cand_cnt(nq), flags(nq);
+    // MRB_SIM_KERNEL=dmma selects the fp64 mma.sync candidate kernel (the round-1 path, kept as
+    // the A/B baseline); the default is the tcgen05 / TMA / TMEM kernel of similarity_tc.cu --
+    // two passes with a fixed per-row threshold for catalogues of 128 ... 512 tiles
+    // (MRB_SIM_KERNEL=tc1 forces its one-pass online top-64 variant), one pass otherwise
+    const char* which = std::getenv("MRB_SIM_KERNEL");
+    const std::string mode = which != nullptr ? which : "";
+    const bool use_dmma = mode == "dmma";
+    const bool two_pass = !use_dmma && mode != "tc1" && sim_tc_twopass_applies(n);
+    const int cap = two_pass ? sim_tc_twopass_capacity() : SIM_C;
+    const double eps = use_dmma ? 1e-12 : SIM_TC_EPS;
+    DevBuf<int> cand_id(static_cast<size_t>(nq) * cap), flags(nq);
+    DevBuf<int> cand_cnt(static_cast<size_t>(nq) * (two_pass ? sim_tc_twopass_groups() : 1));
     DevBuf<double> cand_thr(nq);
     DevBuf<int> d_ids(static_cast<size_t>(nq) * topk);
     DevBuf<double> d_scores(static_cast<size_t>(nq) * topk);
@@ -420,14 +502,9 @@ SimResult cosine_topk(const double* M, int n, int k, int topk, int q_lo, int q_h
     MRB_CUDA(cudaEventRecord(e0, s));
     k_sim_normalize<<<ceil_div(n, 128), 128, 0, s>>>(d_M.p, n, k, kp, H.p, Hp.p);
     MRB_LAUNCHED(1);
-    // MRB_SIM_KERNEL=dmma selects the fp64 mma.sync candidate kernel (the round-1 path, kept as
-    // the A/B baseline); the default is the tcgen05 / TMA / TMEM kernel of similarity_tc.cu
-    const char* which = std::getenv("MRB_SIM_KERNEL");
-    const bool use_dmma = which != nullptr && std::string(which) == "dmma";
-    const double eps = use_dmma ? 1e-12 : SIM_TC_EPS;
     if (!use_dmma) {
         static_assert(SIM_C == 64, "similarity_tc.cu keeps 64 candidates per query as well");
-        cosine_candidates_tc(H.p, n, k, q_lo, q_hi, cand_id.p, cand_thr.p, cand_cnt.p, s);
+        cosine_candidates_tc(H.p, n, k, q_lo, q_hi, cand_id.p, cand_thr.p, cand_cnt.p, s, two_pass);
     } else
     switch (ks) {
         case 4: launch_candidates<4>(Hp.p, n, q_lo, q_hi, cand_id.p, cand_thr.p, cand_cnt.p, s); break;
@@ -436,8 +513,13 @@ SimResult cosine_topk(const double* M, int n, int k, int topk, int q_lo, int q_h
         default: launch_candidates<16>(Hp.p, n, q_lo, q_hi, cand_id.p, cand_thr.p, cand_cnt.p, s); break;
     }
     MRB_CUDA(cudaEventRecord(e1, s));
-    k_sim_rescore<<<ceil_div(static_cast<long long>(nq) * 32, 256), 256, 0, s>>>(
-        H.p, n, k, topk, q_lo, q_hi, cand_id.p, cand_thr.p, cand_cnt.p, d_ids.p, d_scores.p, flags.p, eps);
+    if (two_pass)
+        k_sim_rescore_wide<<<ceil_div(static_cast<long long>(nq) * 32, 256), 256, 0, s>>>(
+            H.p, n, k, topk, q_lo, q_hi, cand_id.p, cand_thr.p, cand_cnt.p, cap, sim_tc_twopass_groups(), d_ids.p,
+            d_scores.p, flags.p, eps);
+    else
+        k_sim_rescore<<<ceil_div(static_cast<long long>(nq) * 32, 256), 256, 0, s>>>(
+            H.p, n, k, topk, q_lo, q_hi, cand_id.p, cand_thr.p, cand_cnt.p, d_ids.p, d_scores.p, flags.p, eps);
     MRB_LAUNCHED(1);
     MRB_CUDA(cudaGetLastError());
     std::vector<int> h_flags(nq);

@@ -20,8 +20,11 @@ SimResult cosine_topk(const double* M, int n, int k, int topk, int q_lo, int q_h
 // normalised rows.  Candidate scores are within SIM_TC_EPS of the exact ones.
 constexpr double SIM_TC_EPS = 1.0e-3;
 void cosine_candidates_tc(const double* d_H, int n, int k, int q_lo, int q_hi, int* cand_id,
-                          double* cand_thr, int* cand_cnt, cudaStream_t s);
+                          double* cand_thr, int* cand_cnt, cudaStream_t s, bool two_pass);
 int sim_tc_candidates();
 int sim_tc_padded_k();
+int sim_tc_twopass_capacity();        // candidate slots per query of the two-pass path (4 x 48)
+int sim_tc_twopass_groups();          // ... in this many per-column-group lists with their own counts
+bool sim_tc_twopass_applies(int n);   // catalogues of 128 .. 512 tiles of 128 rows
 
 }  // namespace mrb

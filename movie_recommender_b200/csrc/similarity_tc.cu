@@ -43,19 +43,36 @@ constexpr int TC_STAGES = 2;
 constexpr int TC_ACC = 4;          // accumulator buffers in TMEM
 constexpr int TC_C = 64;           // candidates kept per query (== SIM_C of similarity.cu)
 constexpr int TC_PEND = 32;        // pending buffer per query
-constexpr int TC_THREADS = 192;    // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+// warp 0 TMA, warp 1 MMA, then SETS groups of 4 epilogue warps (one per TMEM lane quarter).  The
+// one-pass mode keeps per-row lists in shared memory and needs one owner thread per row; the
+// two-pass modes keep nothing per row, so 4 groups split every tile's 8 chunks of 16 columns:
+// 4 warps per scheduler hide the TMEM / vote latencies a single warp per scheduler exposes
+// (one group: 2.9 ms for the collect pass at config 4, profiles/launches_sim_r02.csv).
+template <int MODE> constexpr int tc_sets() { return MODE == 0 ? 1 : 4; }
+template <int MODE> constexpr int tc_threads() { return 64 + 128 * tc_sets<MODE>(); }
 constexpr int TC_TILE_BYTES = TC_N * TC_KB * 4;          // one K block of one tile: 16 KB
 
-struct TcSmem {
+// MODE_TOPK keeps the per-row candidate lists in shared memory (2 catalogue stages fit beside
+// them); the two-pass modes keep nothing per row and use the room for a deeper TMA ring.
+enum { MODE_TOPK = 0, MODE_TILEMAX = 1, MODE_COLLECT = 2 };
+constexpr int TC_SETS2 = 4;        // epilogue warp groups of the two-pass modes (= column groups per tile)
+constexpr int TC_CAPS = 48;        // candidate capacity per (query, column group): ~17 expected
+constexpr int TC_CAP2 = TC_SETS2 * TC_CAPS;
+
+template <int MODE>
+struct TcSmemT {
+    static constexpr int STAGES = MODE == MODE_TOPK ? TC_STAGES : 4;
+    static constexpr int LROWS = MODE == MODE_TOPK ? TC_M : 1;
     alignas(1024) float a[2][TC_M * TC_KB];              // query tile, two K blocks
-    alignas(1024) float b[TC_STAGES][2][TC_N * TC_KB];   // catalogue stages
-    float score[TC_M][TC_C + TC_PEND];                   // [0,64) sorted list, [64,96) pending
-    int id[TC_M][TC_C + TC_PEND];
-    unsigned long long full_bar[TC_STAGES], empty_bar[TC_STAGES];
+    alignas(1024) float b[STAGES][2][TC_N * TC_KB];      // catalogue stages
+    float score[LROWS][TC_C + TC_PEND];                  // [0,64) sorted list, [64,96) pending
+    int id[LROWS][TC_C + TC_PEND];
+    unsigned long long full_bar[STAGES], empty_bar[STAGES];
     unsigned long long acc_full[TC_ACC], acc_empty[TC_ACC];
     unsigned long long a_bar;
     unsigned tmem_base;
 };
+using TcSmem = TcSmemT<MODE_TOPK>;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
     return static_cast<unsigned>(__cvta_generic_to_shared(p));
@@ -190,19 +207,31 @@ __device__ __forceinline__ void tc_merge_row(TcSmem& sm, int row, int lc, int pc
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_sim_candidates_tc(const __grid_constant__ CUtensorMap map, int n, int ksteps, int q_lo, int q_hi,
-                    int* __restrict__ cand_id, double* __restrict__ cand_thr,
-                    int* __restrict__ cand_cnt) {
+// MODE_TOPK    one pass: per-row top-64 kept online (pending buffers + warp merges).  Any n.
+// MODE_TILEMAX pass 1 of 2: tile_max[tile][row] = the row's largest score in each catalogue tile.
+//              The 64th largest tile maximum of a row is a LOWER BOUND of its 64th largest score
+//              (64 tiles each hold a score that large), and at most a handful of scores more can
+//              exceed it (two in one tile).
+// MODE_COLLECT pass 2 of 2: with that bound as a FIXED threshold, append every column whose score
+//              reaches it (~70 per row) to the row's list in global memory -- no sorting, no
+//              merging, no moving threshold in the hot loop.  The GEMM runs twice; it is the
+//              cheap part.
+template <int MODE>
+__global__ void __launch_bounds__(tc_threads<MODE>(), 1)
+k_sim_tc(const __grid_constant__ CUtensorMap map, int n, int ksteps, int q_lo, int q_hi,
+         int* __restrict__ cand_id, double* __restrict__ cand_thr, int* __restrict__ cand_cnt,
+         float* __restrict__ tile_max, int rows_pad, const float* __restrict__ thr0) {
+    using Smem = TcSmemT<MODE>;
+    constexpr int STAGES = Smem::STAGES;
     extern __shared__ unsigned char smem_raw[];
-    TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_base = q_lo + blockIdx.x * TC_M;
     const int ntiles = (n + TC_N - 1) / TC_N;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&sm.full_bar[s], 1); mbar_init(&sm.empty_bar[s], 1); }
-        for (int a = 0; a < TC_ACC; a++) { mbar_init(&sm.acc_full[a], 1); mbar_init(&sm.acc_empty[a], 4); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&sm.full_bar[s], 1); mbar_init(&sm.empty_bar[s], 1); }
+        for (int a = 0; a < TC_ACC; a++) { mbar_init(&sm.acc_full[a], 1); mbar_init(&sm.acc_empty[a], 4 * tc_sets<MODE>()); }
         mbar_init(&sm.a_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -223,8 +252,8 @@ k_sim_candidates_tc(const __grid_constant__ CUtensorMap map, int n, int ksteps, 
             tma_load_2d(sm.a[0], &map, 0, q_base, &sm.a_bar);
             tma_load_2d(sm.a[1], &map, TC_KB, q_base, &sm.a_bar);
             for (int t = 0; t < ntiles; t++) {
-                const int s = t % TC_STAGES;
-                if (t >= TC_STAGES) mbar_wait(&sm.empty_bar[s], ((t / TC_STAGES) - 1) & 1);
+                const int s = t % STAGES;
+                if (t >= STAGES) mbar_wait(&sm.empty_bar[s], ((t / STAGES) - 1) & 1);
                 mbar_expect_tx(&sm.full_bar[s], 2 * TC_TILE_BYTES);
                 tma_load_2d(sm.b[s][0], &map, 0, t * TC_N, &sm.full_bar[s]);
                 tma_load_2d(sm.b[s][1], &map, TC_KB, t * TC_N, &sm.full_bar[s]);
@@ -235,9 +264,9 @@ k_sim_candidates_tc(const __grid_constant__ CUtensorMap map, int n, int ksteps, 
         if (lane == 0) {
             mbar_wait(&sm.a_bar, 0);
             for (int t = 0; t < ntiles; t++) {
-                const int s = t % TC_STAGES, a = t % TC_ACC;
+                const int s = t % STAGES, a = t % TC_ACC;
                 if (t >= TC_ACC) mbar_wait(&sm.acc_empty[a], ((t / TC_ACC) - 1) & 1);
-                mbar_wait(&sm.full_bar[s], (t / TC_STAGES) & 1);
+                mbar_wait(&sm.full_bar[s], (t / STAGES) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned d = tmem + a * TC_N;
                 for (int ks = 0; ks < ksteps; ks++) {
@@ -250,6 +279,7 @@ k_sim_candidates_tc(const __grid_constant__ CUtensorMap map, int n, int ksteps, 
         }
     } else {
         // ================= epilogue: thread = query row = TMEM lane =================
+        if constexpr (MODE == MODE_TOPK) {
         const int quarter = warp & 3;                   // the TMEM lanes this warp may touch
         const int row = quarter * 32 + lane;            // local query row
         const int qrow = q_base + row;
@@ -334,6 +364,83 @@ k_sim_candidates_tc(const __grid_constant__ CUtensorMap map, int n, int ksteps, 
                 cand_thr[out_row] = lc == TC_C ? static_cast<double>(sm.score[rl][TC_C - 1]) : -1e300;
             }
         }
+            } else {
+            constexpr int SETS = tc_sets<MODE>();
+            constexpr int CH_PER_SET = (TC_N / 16) / SETS;          // 16-column chunks per group and tile
+            const int quarter = warp & 3;
+            const int set = (warp - 2) >> 2;                        // this warp's column group
+            const int row = quarter * 32 + lane;
+            const int qrow = q_base + row;
+            const bool qvalid = qrow < q_hi;
+            const size_t out_row = static_cast<size_t>(qrow - q_lo);
+            const unsigned lane_base = tmem + (static_cast<unsigned>(quarter * 32) << 16);
+            float thr = 3.0e38f;                                   // MODE_COLLECT: fixed threshold
+            if (MODE == MODE_COLLECT && qvalid) thr = thr0[out_row];
+            int cnt = 0;
+            int* my_list = cand_id + (out_row * SETS + set) * TC_CAPS;
+            for (int t = 0; t < ntiles; t++) {
+                const int a = t % TC_ACC;
+                mbar_wait(&sm.acc_full[a], (t / TC_ACC) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int valid_cols = min(TC_N, n - t * TC_N);
+                const unsigned tbase = lane_base + a * TC_N + set * (CH_PER_SET * 16);
+                const int colbase = t * TC_N + set * (CH_PER_SET * 16);
+                const int limit0 = valid_cols - set * (CH_PER_SET * 16);
+                float va[16], vb[16];
+                float m0 = -3.0e38f, m1 = -3.0e38f;
+                // takers of one 16-score chunk: the chunk maximum first (takers are 0.1 % of the
+                // scores), one vote per chunk, the scan only where the maximum qualifies
+                auto collect = [&](const float (&v)[16], int col0, int limit) {
+                    float m = -3.0e38f;
+                    if (limit >= 16) {
+                        float ma = fmaxf(v[0], v[1]), mb = fmaxf(v[2], v[3]);
+#pragma unroll
+                        for (int j = 4; j < 16; j += 2) { ma = fmaxf(ma, v[j]); mb = fmaxf(mb, v[j + 1]); }
+                        m = fmaxf(ma, mb);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) if (j < limit) m = fmaxf(m, v[j]);
+                    }
+                    if (__any_sync(0xffffffffu, m >= thr)) {
+                        if (m >= thr) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                                if (v[j] >= thr && j < limit) {
+                                    if (cnt < TC_CAPS) my_list[cnt] = col0 + j;
+                                    cnt++;
+                                }
+                        }
+                    }
+                };
+                auto tilemax = [&](const float (&v)[16], int limit) {
+                    if (limit >= 16) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) { m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) if (j < limit) m0 = fmaxf(m0, v[j]);
+                    }
+                };
+                static_assert(CH_PER_SET == 2, "the epilogue below handles exactly two chunks per group");
+                tmem_ld16(tbase, va);
+                tmem_ld16(tbase + 16, vb);
+                tmem_wait_ld(va);
+                if (MODE == MODE_COLLECT) collect(va, colbase, limit0);
+                else tilemax(va, limit0);
+                tmem_wait_ld(vb);
+                if (MODE == MODE_COLLECT) collect(vb, colbase + 16, limit0 - 16);
+                else tilemax(vb, limit0 - 16);
+                if (MODE == MODE_TILEMAX)
+                    tile_max[(static_cast<size_t>(t) * SETS + set) * rows_pad + (qrow - q_lo)] = fmaxf(m0, m1);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.acc_empty[a]);
+            }
+            if (MODE == MODE_COLLECT && qvalid) {
+                cand_cnt[out_row * SETS + set] = cnt;
+                if (set == 0) cand_thr[out_row] = static_cast<double>(thr);
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -373,14 +480,82 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
+// thr0[row] = the 64th largest of the row's tile maxima (one warp per row): bisection on the
+// order-preserving integer image of the floats -- 32 rounds of "how many values reach mid".
+__global__ void __launch_bounds__(256)
+k_sim_select_thr(const float* __restrict__ tile_max, int ntiles, int rows_pad, int nq, int want,
+                 float* __restrict__ thr0) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nq) return;
+    constexpr int PER = 64;                                  // up to 2048 maxima per row in registers
+    unsigned key[PER];
+    const int per = (ntiles + 31) / 32;
+    auto ordered = [](float f) {
+        const unsigned b = __float_as_uint(f);
+        return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    };
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int t = lane + 32 * i;
+        key[i] = (i < per && t < ntiles) ? ordered(tile_max[static_cast<size_t>(t) * rows_pad + w]) : 0u;
+    }
+    auto count_ge = [&](unsigned mid) {
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < PER; i++) c += (key[i] >= mid && key[i] != 0u) ? 1 : 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        return c;
+    };
+    // the largest K with count(key >= K) >= want is the want-th largest key
+    unsigned lo = 1u, hi = 0xffffffffu;                      // invariant: count_ge(lo) >= want
+    if (count_ge(lo) < want) {                               // fewer values than wanted: take everything
+        if (lane == 0) thr0[w] = -3.0e38f;
+        return;
+    }
+    while (lo < hi) {
+        const unsigned mid = lo + ((hi - lo + 1u) >> 1);
+        if (count_ge(mid) >= want) lo = mid;
+        else hi = mid - 1u;
+    }
+    if (lane == 0) {
+        const unsigned b = (lo & 0x80000000u) ? (lo & 0x7fffffffu) : ~lo;
+        thr0[w] = __uint_as_float(b);
+    }
+}
+
+template <int MODE>
+void launch_tc(const CUtensorMap& map, int grid, int n, int ksteps, int q_lo, int q_hi, int* cand_id,
+               double* cand_thr, int* cand_cnt, float* tile_max, int rows_pad, const float* thr0,
+               cudaStream_t s) {
+    const size_t smem = sizeof(TcSmemT<MODE>) + 1024;
+    static bool attr = false;
+    if (!attr) {
+        MRB_CUDA(cudaFuncSetAttribute(k_sim_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+        attr = true;
+    }
+    k_sim_tc<MODE><<<grid, tc_threads<MODE>(), smem, s>>>(map, n, ksteps, q_lo, q_hi, cand_id, cand_thr, cand_cnt,
+                                                  tile_max, rows_pad, thr0);
+    MRB_LAUNCHED(1);
+    MRB_CUDA(cudaGetLastError());
+}
+
 }  // namespace
 
 int sim_tc_candidates() { return TC_C; }
 int sim_tc_padded_k() { return TC_KP; }
+int sim_tc_twopass_capacity() { return TC_CAP2; }
+int sim_tc_twopass_groups() { return TC_SETS2; }
+// the two-pass path needs at least 2 x 64 tile maxima per row for its threshold to be tight
+bool sim_tc_twopass_applies(int n) { return (n + TC_N - 1) / TC_N >= 128 && (n + TC_N - 1) / TC_N <= 512; }
 
-// H: device, n x k normalised rows (fp64).  Fills cand_id[nq][64], cand_thr[nq], cand_cnt[nq].
+// H: device, n x k normalised rows (fp64).
+// one pass (two_pass == false): cand_id[nq][64], cand_thr[nq] = approximate 64th score, cand_cnt[nq];
+// two passes: cand_id[nq][128] = every column whose approximate score reaches cand_thr[nq] (a lower
+// bound of the row's 64th largest approximate score), cand_cnt[nq] (may exceed 128: overflow).
 void cosine_candidates_tc(const double* d_H, int n, int k, int q_lo, int q_hi, int* cand_id,
-                          double* cand_thr, int* cand_cnt, cudaStream_t s) {
+                          double* cand_thr, int* cand_cnt, cudaStream_t s, bool two_pass) {
     MRB_REQUIRE(k >= 1 && k <= TC_KP, "cosine_candidates_tc: factor count must be in 1..64");
     const int nq = q_hi - q_lo;
     if (nq <= 0) return;
@@ -400,17 +575,21 @@ void cosine_candidates_tc(const double* d_H, int n, int k, int q_lo, int q_hi, i
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MRB_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
-    const size_t smem = sizeof(TcSmem) + 1024;
-    static bool attr = false;
-    if (!attr) {
-        MRB_CUDA(cudaFuncSetAttribute(k_sim_candidates_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
-        attr = true;
-    }
     const int ksteps = (k + 7) / 8;
-    k_sim_candidates_tc<<<grid, TC_THREADS, smem, s>>>(map, n, ksteps, q_lo, q_hi, cand_id, cand_thr, cand_cnt);
-    MRB_LAUNCHED(1);
-    MRB_CUDA(cudaGetLastError());
+    if (!two_pass) {
+        launch_tc<MODE_TOPK>(map, grid, n, ksteps, q_lo, q_hi, cand_id, cand_thr, cand_cnt, nullptr, 0, nullptr, s);
+    } else {
+        const int ntiles = ceil_div(n, TC_N), rows_pad = grid * TC_M;
+        DevBuf<float> tile_max(static_cast<size_t>(ntiles) * TC_SETS2 * rows_pad), thr0(nq);
+        launch_tc<MODE_TILEMAX>(map, grid, n, ksteps, q_lo, q_hi, nullptr, nullptr, nullptr, tile_max.p, rows_pad,
+                                nullptr, s);
+        k_sim_select_thr<<<ceil_div(static_cast<long long>(nq) * 32, 256), 256, 0, s>>>(tile_max.p, ntiles * TC_SETS2,
+                                                                                      rows_pad, nq, TC_C, thr0.p);
+        MRB_LAUNCHED(1);
+        launch_tc<MODE_COLLECT>(map, grid, n, ksteps, q_lo, q_hi, cand_id, cand_thr, cand_cnt, nullptr, rows_pad,
+                                thr0.p, s);
+        MRB_CUDA(cudaStreamSynchronize(s));   // tile_max / thr0 are released on return
+    }
     MRB_CUDA(cudaStreamSynchronize(s));   // Hq is released on return
 }
 

@@ -7,6 +7,17 @@ csrc/als_gram.cu) started from zero factors.
 
 A user needs at least ``k+1`` usable ratings (models.py:669, :694) -- others are returned as
 invalid (NaN rows), like the reference's ``_valid = False``.
+
+Two deliberate differences from ``ALS_Model`` (models.py:669-697):
+
+* the reference counts only the ratings whose movie has ALS factors (it filters through
+  ``als_movie_ids`` first); here ``item_ids`` already ARE rows of ``item_factors``, so the caller
+  does that filtering when it maps raw movie ids -- the validity test is applied to what is
+  passed in;
+* a rank-deficient system (``k+1`` or more ratings that do not determine every unknown) gets the
+  pivot-skipping Cholesky solution -- undetermined unknowns stay at 0, the rest is solved
+  consistently -- where ``numpy.linalg.lstsq`` returns the minimum-norm solution.  Both fit the
+  given ratings equally well; the factors differ.  Such users are still reported valid.
 """
 import numpy
 

@@ -47,14 +47,20 @@ class ShardedAls:
     ``all_gather`` of the ranges after each half-sweep."""
 
     def __init__(self, problem, k, num_users, num_items, rank, world, exchange="p2p",
-                 async_upload=False, partition=None):
+                 async_upload=False, partition=None, sliced_arrays=False):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.rank, self.world, self.k = rank, world, k
         self.nu, self.ni = num_users, num_items
         self.exchange = exchange
-        self.nnz = len(problem["ratings"])
+        # sliced_arrays: problem["user_ids" / "item_ids" / "ratings"] are THIS RANK'S slice of a
+        # problem of problem["num_ratings_total"] ratings starting at problem["slice_begin"], and
+        # problem["user_factors_rows" / "item_factors_rows"] hold just the factor rows of
+        # problem["user_rows" / "item_rows"] -- no process holds the whole problem on the host
+        # (config 5: 16 GB of ratings, 10 GB of user factors)
+        self.sliced_arrays = sliced_arrays
+        self.nnz = int(problem["num_ratings_total"]) if sliced_arrays else len(problem["ratings"])
         self.partition = (1 if exchange == "p2p" else 0) if partition is None else partition
         import os
         import time
@@ -62,24 +68,41 @@ class ShardedAls:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.u_rows = io_slice(num_users, rank, world)
         self.i_rows = io_slice(num_items, rank, world)
+        if sliced_arrays:
+            if exchange != "p2p":
+                raise ValueError("sliced host arrays need the peer-to-peer path")
+            self.u_rows, self.i_rows = tuple(problem["user_rows"]), tuple(problem["item_rows"])
         if exchange == "p2p":
-            self.prob = cpp_ls.AlsProblem(problem["user_ids"], problem["item_ids"], problem["ratings"],
-                                          k, num_users, num_items,
-                                          coo_slice=io_slice(self.nnz, rank, world))
+            if sliced_arrays:
+                b = int(problem["slice_begin"])
+                self.prob = cpp_ls.AlsProblem(problem["user_ids"], problem["item_ids"], problem["ratings"],
+                                              k, num_users, num_items,
+                                              coo_slice=(b, b + len(problem["ratings"])), total_ratings=self.nnz)
+            else:
+                self.prob = cpp_ls.AlsProblem(problem["user_ids"], problem["item_ids"], problem["ratings"],
+                                              k, num_users, num_items,
+                                              coo_slice=io_slice(self.nnz, rank, world))
             marks.append(("create (slice upload enqueued)", time.time()))
-            mine = torch.frombuffer(bytearray(self.prob.ipc_handles_all()), dtype=torch.uint8).to(self.device)
-            allh = torch.empty(384 * world, dtype=torch.uint8, device=self.device)
-            dist.all_gather_into_tensor(allh, mine)
-            allh = bytes(allh.cpu().numpy())
+            if world > 1:
+                mine = torch.frombuffer(bytearray(self.prob.ipc_handles_all()), dtype=torch.uint8).to(self.device)
+                allh = torch.empty(384 * world, dtype=torch.uint8, device=self.device)
+                dist.all_gather_into_tensor(allh, mine)
+                allh = bytes(allh.cpu().numpy())
+            else:
+                allh = self.prob.ipc_handles_all()
             marks.append(("handle exchange", time.time()))
             self.prob.open_peer_group([allh[384 * r:384 * (r + 1)] for r in range(world)], rank,
                                       self.partition)
             marks.append(("open peers", time.time()))
             self.prob.push_coo()            # own slice -> every peer (NVLink)
             self.prob.peer_barrier()        # problem stream: every rank's slice is everywhere
-            uf0 = problem["user_factors0"].reshape(-1)
-            itf0 = problem["item_factors0"].reshape(-1)
-            self.prob.upload_factor_rows(uf0, itf0, *self.u_rows, *self.i_rows)
+            if sliced_arrays:
+                self.prob.upload_factor_rows(problem["user_factors_rows"], problem["item_factors_rows"],
+                                             *self.u_rows, *self.i_rows, rows_only=True)
+            else:
+                uf0 = problem["user_factors0"].reshape(-1)
+                itf0 = problem["item_factors0"].reshape(-1)
+                self.prob.upload_factor_rows(uf0, itf0, *self.u_rows, *self.i_rows)
             self.prob.build_index()         # id check, both groupings, this rank's work lists
             marks.append(("index + work lists", time.time()))
             # second barrier, on the stream the sweeps use and behind this rank's factor pushes:
@@ -142,6 +165,12 @@ class ShardedAls:
         host arrays; the union over ranks is the whole result."""
         stream = self.torch.cuda.current_stream().cuda_stream
         self.prob.download_factor_rows(user_factors, item_factors, *self.u_rows, *self.i_rows, stream)
+
+    def download_own_rows_into(self, user_rows_array, item_rows_array):
+        """The same with arrays that hold just this rank's I/O rows (``sliced_arrays`` problems)."""
+        stream = self.torch.cuda.current_stream().cuda_stream
+        self.prob.download_factor_rows(user_rows_array, item_rows_array, *self.u_rows, *self.i_rows,
+                                       stream, rows_only=True)
 
     def bench(self, algorithm, warmup, steps, sampler=None):
         torch, dist = self.torch, self.dist

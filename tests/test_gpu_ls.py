@@ -130,3 +130,22 @@ def test_ls_native_ragged_empty_and_termination(require_gpu, cpp_ls, oracle):
         xo, ito, rro = oracle.cg_least_squares(rowptr, col, vals, cols, b, x0, mrd, maxit, thread_count=1)
         assert it == ito and _rel(x, xo) < 1e-6, (mrd, maxit)
         assert bits_equal(x.reshape(-1)[-10:], x0[-10:])      # empty columns keep x0
+
+
+def test_malformed_csr_is_refused(require_gpu, cpp_ls):
+    """A column index outside [0, columns) or decreasing row pointers raise CppLsError instead of
+    becoming an out-of-bounds device access; the library keeps working afterwards."""
+    from movie_recommender_b200._lib import CppLsError
+    rowptr = np.array([0, 2, 4], dtype=np.int32)
+    col = np.array([0, 1, 1, 7], dtype=np.int32)           # 7 >= 3 columns
+    vals = np.ones(4)
+    b = np.ones(2)
+    for alg in (1, 2, 3):
+        with pytest.raises(CppLsError):
+            cpp_ls.cg_least_squares(rowptr, col, vals, 3, b, algorithm=alg, x0=np.zeros(3))
+    bad_ptr = np.array([0, 3, 2], dtype=np.int32)
+    with pytest.raises(CppLsError):
+        cpp_ls.cg_least_squares(bad_ptr, col[:2], vals[:2], 3, b, algorithm=3, x0=np.zeros(3))
+    col[3] = 2
+    x, it, rr = cpp_ls.cg_least_squares(rowptr, col, vals, 3, b, algorithm=1, x0=np.zeros(3))
+    assert np.all(np.isfinite(x))

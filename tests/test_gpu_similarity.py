@@ -18,8 +18,8 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(autouse=True, params=["tcgen05", "dmma"])
 def candidate_kernel(request):
     old = os.environ.get("MRB_SIM_KERNEL")
-    if request.param == "dmma":
-        os.environ["MRB_SIM_KERNEL"] = "dmma"
+    if request.param != "tcgen05":
+        os.environ["MRB_SIM_KERNEL"] = request.param
     else:
         os.environ.pop("MRB_SIM_KERNEL", None)
     yield request.param
@@ -43,6 +43,30 @@ def test_topk_ids_and_scores_bitexact(require_gpu, oracle, n, k, topk):
     oi, os_ = oracle.cosine_topk(M, topk)
     assert np.array_equal(ids, oi)
     assert bits_equal(scores, os_)
+
+
+@pytest.mark.parametrize("mode", ["two-pass", "tc1"])
+def test_large_catalogue_two_pass_and_one_pass(require_gpu, oracle, mode, monkeypatch):
+    """Catalogues of >= 128 tiles take the two-pass tcgen05 path (tile maxima -> fixed per-row
+    threshold -> collect); MRB_SIM_KERNEL=tc1 forces the one-pass online top-64 kernel.  Whole
+    result against properties, sampled query blocks against the oracle, incl. duplicates."""
+    if os.environ.get("MRB_SIM_KERNEL") == "dmma":
+        pytest.skip("the fp64 kernel is covered by the other tests")
+    if mode == "tc1":
+        monkeypatch.setenv("MRB_SIM_KERNEL", "tc1")
+    n, k, topk = 17000, 50, 50
+    rng = np.random.default_rng(17)
+    M = rng.standard_normal((n, k))
+    M[5000:5040] = M[5000]                      # 40 identical rows: ties at the top
+    M[123] = 0.0
+    ids, scores, info = sim().factor_cosine_topk(M, topk=topk)
+    assert ids.shape == (n, topk) and np.all(ids != np.arange(n)[:, None])
+    assert np.all(np.diff(scores, axis=1) <= 0)
+    for lo, hi in [(0, 48), (4990, 5050), (11111, 11143), (n - 20, n)]:
+        oi, os_ = oracle.cosine_topk(M, topk, lo, hi)
+        assert np.array_equal(ids[lo:hi], oi) and bits_equal(scores[lo:hi], os_)
+    part = sim().factor_cosine_topk(M, topk=topk, q_lo=4000, q_hi=4300)
+    assert np.array_equal(part[0], ids[4000:4300]) and bits_equal(part[1], scores[4000:4300])
 
 
 def test_duplicates_and_ties_force_the_exact_fallback(require_gpu, oracle):

@@ -118,10 +118,22 @@ def bench(args, sampler, rank, world):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(sse)
     launches = (cpp_ls.kernel_launches() - l0) * world
-    t0 = time.time()
     runner.download_own_rows_into(uf_rows, itf_rows)
-    down_s = time.time() - t0
     timed_out = cpp_ls._dll.mrb_peer_barrier_timed_out()
+    runner.close()
+    # ---- end to end from the host slices, with the device arena warm (the first construction of
+    # a process pays cudaMalloc for ~80 GB of buffers): construction [slice upload, NVLink push,
+    # index build, work lists] + one sweep + download of this rank's factor rows
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    runner = sharded.ShardedAls(problem, k, nu, ni, rank, world, sliced_arrays=True)
+    runner.sweep()
+    runner.download_own_rows_into(uf_rows, itf_rows)
+    e2e_t = torch.tensor([time.time() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     runner.close()
     cpp_ls._dll.mrb_trim_memory()
 
@@ -186,7 +198,7 @@ def bench(args, sampler, rank, world):
     tf = flops / (gram_ms / args.steps * 1e-3) / 1e12
     hbm, hbm_src = load_peaks()
     alg_bytes = total * (4 + 8 + 8 * k) + total * (4 + 8 + 8 * (k + 1)) + (nu * n_u + ni * n_i) * 16
-    e2e_s = float(ms[2]) * 1e-3 + step_ms * 1e-3 + down_s
+    e2e_s = float(e2e_t[0])
     out = {"metric": "als_ratings_per_sec_per_sweep", "value": total / (step_ms * 1e-3), "unit": "ratings/s",
            "ms_per_step": step_ms, "dtype": "f64", "scaling": "strong",
            "data": "synthetic (seeded %d): power-law users x Zipf movies, pairs drawn with replacement, "
