@@ -61,7 +61,6 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
     user_ids_.alloc(nnz);
     item_ids_.alloc(nnz);
     ratings_.alloc(nnz);
-    rmb_.alloc(nnz);
     u_ptr_.alloc(static_cast<size_t>(nu_) + 1);
     i_ptr_.alloc(static_cast<size_t>(ni_) + 1);
     u_idx_.alloc(nnz);
@@ -263,6 +262,8 @@ AlsRunInfo AlsProblem::run(int algorithm, double min_r_decrease, int max_iterati
 AlsRunInfo AlsProblem::run_faithful(int algorithm, double min_r_decrease, int max_iteration,
                                     int T) {
     const int n = k_ + 1;
+    build_index();
+    if (rmb_.n != static_cast<size_t>(nnz_)) rmb_.alloc(nnz_);   // rating - user bias, reference-order modes only
     wait_ratings();
     wait_factors();
     AlsFaithfulOp user_op(nnz_, nu_, user_ids_.p, item_ids_.p, u_ptr_.p, u_idx_.p, itf_.p, n, k_,

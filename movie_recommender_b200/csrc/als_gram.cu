@@ -88,6 +88,15 @@ __device__ __forceinline__ int work_index(int w, int n_work, int mode) {
 
 __device__ double g_zero_row[176];   // zero-initialised: the factor row of a padding rating
 
+// The id / rating streams are read exactly once per half-sweep: GRAM_STREAM_IDS loads them with the
+// evict-first policy (ld.global.cs) so that they do not push the gathered factor rows -- the only
+// data with reuse -- out of L2 (movie side: 116 MB of user factors against 126 MB of L2).
+#ifdef GRAM_STREAM_IDS
+#define GRAM_LD_ID(ptr) __ldcs(ptr)
+#else
+#define GRAM_LD_ID(ptr) (*(ptr))
+#endif
+
 template <int M8, bool USER, int EPI>
 // (no minimum-CTAs argument: naming even the default "1" changes ptxas' schedule of the movie-side
 // kernel -- 4.47 instead of 3.73 ms per launch at C3, profiles/ab_tree_r02.log; forcing 3 CTAs per
@@ -157,17 +166,17 @@ k_gram(const GramArgs A) {
         const int nsteps = (cnt + 3) >> 2;
         int ids_cur = 0, ids_nxt = 0;
         double rts_cur = 0, rts_nxt = 0;
-        if (lane < cnt) { ids_cur = A.other_g[wi.beg + lane]; rts_cur = A.rating_g[wi.beg + lane]; }
-        if (32 + lane < cnt) { ids_nxt = A.other_g[wi.beg + 32 + lane]; rts_nxt = A.rating_g[wi.beg + 32 + lane]; }
+        if (lane < cnt) { ids_cur = GRAM_LD_ID(A.other_g + wi.beg + lane); rts_cur = GRAM_LD_ID(A.rating_g + wi.beg + lane); }
+        if (32 + lane < cnt) { ids_nxt = GRAM_LD_ID(A.other_g + wi.beg + 32 + lane); rts_nxt = GRAM_LD_ID(A.rating_g + wi.beg + 32 + lane); }
         // a third batch in flight: with only one batch ahead the k-steps ran into the latency
         // of the id / rating streams (HBM) every 8 steps (11.2 -> 10.5 ms per sweep at C3)
         int ids_nx2 = 0;
         double rts_nx2 = 0;
-        if (64 + lane < cnt) { ids_nx2 = A.other_g[wi.beg + 64 + lane]; rts_nx2 = A.rating_g[wi.beg + 64 + lane]; }
+        if (64 + lane < cnt) { ids_nx2 = GRAM_LD_ID(A.other_g + wi.beg + 64 + lane); rts_nx2 = GRAM_LD_ID(A.rating_g + wi.beg + 64 + lane); }
 #ifdef GRAM_ID_BATCHES4
         int ids_nx3 = 0;
         double rts_nx3 = 0;
-        if (96 + lane < cnt) { ids_nx3 = A.other_g[wi.beg + 96 + lane]; rts_nx3 = A.rating_g[wi.beg + 96 + lane]; }
+        if (96 + lane < cnt) { ids_nx3 = GRAM_LD_ID(A.other_g + wi.beg + 96 + lane); rts_nx3 = GRAM_LD_ID(A.rating_g + wi.beg + 96 + lane); }
 #endif
         // prep(st): the row pointer and rating of k-step `st` (ratings 4 st .. 4 st + 3) from the
         // id batches; st's batch is the current or the next one
@@ -212,12 +221,12 @@ k_gram(const GramArgs A) {
                 const int e = (step << 2) + 96 + lane;
                 ids_nx3 = 0;
                 rts_nx3 = 0;
-                if (e < cnt) { ids_nx3 = A.other_g[wi.beg + e]; rts_nx3 = A.rating_g[wi.beg + e]; }
+                if (e < cnt) { ids_nx3 = GRAM_LD_ID(A.other_g + wi.beg + e); rts_nx3 = GRAM_LD_ID(A.rating_g + wi.beg + e); }
 #else
                 const int e = (step << 2) + 64 + lane;
                 ids_nx2 = 0;
                 rts_nx2 = 0;
-                if (e < cnt) { ids_nx2 = A.other_g[wi.beg + e]; rts_nx2 = A.rating_g[wi.beg + e]; }
+                if (e < cnt) { ids_nx2 = GRAM_LD_ID(A.other_g + wi.beg + e); rts_nx2 = GRAM_LD_ID(A.rating_g + wi.beg + e); }
 #endif
             }
             if (step + RD - 1 < nsteps) {
@@ -1129,6 +1138,9 @@ void AlsProblem::launch_half(bool user_side, cudaStream_t stream, int epilogue) 
     gram_events_.push_back(e0);
     MRB_CUDA(cudaEventCreate(&e1));
     gram_events_.push_back(e1);
+    // (Measured and rejected, profiles/ab_ids_r02.log: a persisting-L2 access-policy window on the
+    // gathered factor matrix -- movie side 3.80 vs 3.76 ms -- and evict-first loads of the id /
+    // rating streams, GRAM_STREAM_IDS -- 3.75 vs 3.76 ms: the launch is not waiting on L2 misses.)
     MRB_CUDA(cudaEventRecord(e0, stream));
     if (epilogue == EPI_STORE) {
         // rows without ratings are not in the work list: their blocks must read as zero

@@ -71,6 +71,9 @@ __device__ __forceinline__ int wide_at(int i, int j) {
 // loop of gram_solve restricted to the tiles D and W): on return D = L_d (lower part), W = L_d^-T.
 // npiv < 8 only in the last tile column (index n, the right-hand side, is not a pivot); *corner
 // receives element (npiv, npiv) before the scaling -- the residual corner -- on every lane.
+// (Measured and rejected: every lane holding the whole 8x8 tile and factoring it redundantly in
+// registers, no shuffles, results through a 1 KB scratch -- 58.3 vs 56.5 ms on the user side of
+// a 27 M-rating k = 128 problem: the scalar chain is no shorter than the shuffle round trips.)
 __device__ __forceinline__ void wide_factor_diag(double& d0, double& d1, double& w0, double& w1,
                                                  double thr, int npiv, int lane, double* corner) {
     const int p = lane >> 2, q = lane & 3;
@@ -195,7 +198,11 @@ __device__ __forceinline__ void wide_accumulate(const GramArgs& A, const WorkIte
         for (int t = 0; t < R1; t++) {
             const int j = 8 * t + p;
             double v = srow[j];                                   // raw factor (0 beyond the row)
-            if (8 * t + 7 >= k) {                                 // tiles that hold special elements
+            // only the last two (users) / the last (movies) tiles can hold special elements: the
+            // order k + 2 (k + 1) fills the last tile, so every tile before them is plain -- a
+            // compile-time fact (a run-time test on k cost a select per element of EVERY tile:
+            // 30 % of the accumulation's instructions, profiles/ncu_k_gram_wide_k128_r02_v2.txt)
+            if (t >= (USER ? M8 - 2 : M8 - 1)) {
                 if (USER) v = j < k ? v : (!valid ? 0.0 : (j == k ? 1.0 : (j == k + 1 ? rt : 0.0)));
                 else v = j < k ? v : ((valid && j == k) ? rt - v : 0.0);   // rating - user bias (matrix.cpp:1029)
             }

@@ -353,15 +353,23 @@ k_sim_rescore_wide(const double* __restrict__ H, int n, int k, int topk, int q_l
         if (lane == 0) flags[w] = 1;
         return;
     }
+    // the `groups` lists are read as ONE dense list: position pos -> (list, offset) through the
+    // running sums of the counts, so the ~66 candidates fill 3 register slots per lane instead of
+    // being strewn over 6
     constexpr int PER = 6;                 // cap <= 192
+    int start[5] = {0, 0, 0, 0, 0};        // groups <= 4
+    for (int g = 0; g < groups && g < 4; g++) start[g + 1] = start[g] + cand_cnt[static_cast<size_t>(w) * groups + g];
+    const int total = start[groups < 4 ? groups : 4];
     double s[PER];
     int id[PER];
 #pragma unroll
     for (int e = 0; e < PER; e++) {
-        const int slot = lane + 32 * e;
-        const int g = slot / sub, within = slot - g * sub;
-        id[e] = (slot < cap && within < cand_cnt[static_cast<size_t>(w) * groups + g])
-                    ? cand_id[static_cast<size_t>(w) * cap + slot] : -1;
+        const int pos = lane + 32 * e;
+        id[e] = -1;
+        if (pos < total) {
+            const int g = (pos >= start[1]) + (pos >= start[2]) + (pos >= start[3]);
+            id[e] = cand_id[static_cast<size_t>(w) * cap + g * sub + (pos - start[g])];
+        }
         if (id[e] == qrow) id[e] = -1;     // the query itself rides along in the candidate list
         s[e] = id[e] >= 0 ? exact_score(a, H + static_cast<size_t>(id[e]) * k, k) : -1e300;
     }

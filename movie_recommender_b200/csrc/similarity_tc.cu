@@ -483,21 +483,29 @@ EncodeTiledFn encode_tiled() {
 // thr0[row] = the 64th largest of the row's tile maxima (one warp per row): bisection on the
 // order-preserving integer image of the floats -- 32 rounds of "how many values reach mid".
 __global__ void __launch_bounds__(256)
-k_sim_select_thr(const float* __restrict__ tile_max, int ntiles, int rows_pad, int nq, int want,
+k_sim_select_thr(const float* __restrict__ tile_max, int ntiles, int sets, int rows_pad, int nq, int want,
                  float* __restrict__ thr0) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= nq) return;
-    constexpr int PER = 64;                                  // up to 2048 maxima per row in registers
+    constexpr int PER = 16;                                  // up to 512 tiles per row in registers
     unsigned key[PER];
     const int per = (ntiles + 31) / 32;
     auto ordered = [](float f) {
         const unsigned b = __float_as_uint(f);
         return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
     };
+    // one value per tile: the largest of its column groups' maxima (a bound from WHOLE tiles is a
+    // little looser than one from quarter tiles, and four times cheaper to select from)
 #pragma unroll
     for (int i = 0; i < PER; i++) {
         const int t = lane + 32 * i;
-        key[i] = (i < per && t < ntiles) ? ordered(tile_max[static_cast<size_t>(t) * rows_pad + w]) : 0u;
+        key[i] = 0u;
+        if (i < per && t < ntiles) {
+            float m = -3.0e38f;
+            for (int g = 0; g < sets; g++)
+                m = fmaxf(m, tile_max[(static_cast<size_t>(t) * sets + g) * rows_pad + w]);
+            key[i] = ordered(m);
+        }
     }
     auto count_ge = [&](unsigned mid) {
         int c = 0;
@@ -583,7 +591,7 @@ void cosine_candidates_tc(const double* d_H, int n, int k, int q_lo, int q_hi, i
         DevBuf<float> tile_max(static_cast<size_t>(ntiles) * TC_SETS2 * rows_pad), thr0(nq);
         launch_tc<MODE_TILEMAX>(map, grid, n, ksteps, q_lo, q_hi, nullptr, nullptr, nullptr, tile_max.p, rows_pad,
                                 nullptr, s);
-        k_sim_select_thr<<<ceil_div(static_cast<long long>(nq) * 32, 256), 256, 0, s>>>(tile_max.p, ntiles * TC_SETS2,
+        k_sim_select_thr<<<ceil_div(static_cast<long long>(nq) * 32, 256), 256, 0, s>>>(tile_max.p, ntiles, TC_SETS2,
                                                                                       rows_pad, nq, TC_C, thr0.p);
         MRB_LAUNCHED(1);
         launch_tc<MODE_COLLECT>(map, grid, n, ksteps, q_lo, q_hi, cand_id, cand_thr, cand_cnt, nullptr, rows_pad,

@@ -73,6 +73,11 @@ class ShardedAls:
                 raise ValueError("sliced host arrays need the peer-to-peer path")
             self.u_rows, self.i_rows = tuple(problem["user_rows"]), tuple(problem["item_rows"])
         if exchange == "p2p":
+            # the device-side barriers below spin (with a 10 s timeout) until every rank has
+            # arrived: enter the construction together, however long each rank's host-side
+            # preparation took
+            if world > 1:
+                dist.barrier()
             if sliced_arrays:
                 b = int(problem["slice_begin"])
                 self.prob = cpp_ls.AlsProblem(problem["user_ids"], problem["item_ids"], problem["ratings"],
