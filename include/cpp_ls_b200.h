@@ -267,6 +267,10 @@ MRB_API int mrb_cosim_create(int num_movies, int num_users, const int* m_ptr, co
 MRB_API int mrb_cosim_query(mrb_cosim* h, int q_lo, int q_hi, const double* buff, int buff_len,
                             int num_results, int* out_idx, double* out_score, int* out_count,
                             float* kernel_ms);
+/* One pair of movies (list indices): the number of common raters and the cosine of their ratings
+ * over them (0 when fewer than 3) -- _scaled_dot_product, build_similar_movies_db.py:72-107,
+ * which tune() (:183-221) calls between queries. */
+MRB_API int mrb_cosim_pair(mrb_cosim* h, int a, int b, int* common_raters, double* similarity);
 MRB_API void mrb_cosim_destroy(mrb_cosim* h);
 
 /* ------------------------------------------------------------------------------------------

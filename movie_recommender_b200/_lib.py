@@ -148,6 +148,8 @@ def _declare(dll):
     dll.mrb_cosim_query.restype = c_int
     dll.mrb_cosim_query.argtypes = [c_void_p, c_int, c_int, _D, c_int, c_int, _I, _D, _I,
                                     ctypes.POINTER(ctypes.c_float)]
+    dll.mrb_cosim_pair.restype = c_int
+    dll.mrb_cosim_pair.argtypes = [c_void_p, c_int, c_int, _I, _D]
     dll.mrb_cosim_destroy.restype = None
     dll.mrb_cosim_destroy.argtypes = [c_void_p]
     dll.mrb_movie_medians.restype = c_int

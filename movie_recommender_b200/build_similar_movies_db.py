@@ -156,19 +156,21 @@ class SimilarMovieFinder:
         return idx, score, count[:nq]
 
     # ------------------------------------------------------------------ the reference's methods
+    def _pair(self, a, b):
+        """Device call: (common raters, cosine over them) of movies ``a`` and ``b``."""
+        n = ctypes.c_int(0)
+        sim = ctypes.c_double(0.0)
+        _lib.check(_dll.mrb_cosim_pair(self._h, a, b, ctypes.byref(n), ctypes.byref(sim)))
+        return n.value, sim.value
+
     def _scaled_dot_product(self, movie_id1_index, movie_id2_index):
-        """(final_score, common_reviewers, pre_boost_score) of one pair (:72-119); host side,
-        used by ``tune`` exactly as in the reference."""
-        ratings1 = self.movie_ratings[movie_id1_index][1]
-        ratings2 = self.movie_ratings[movie_id2_index][1]
-        if len(ratings1) > len(ratings2):
-            ratings1, ratings2 = ratings2, ratings1
-        r1 = [ratings1[u] for u in ratings1 if u in ratings2]
-        r2 = [ratings2[u] for u in ratings1 if u in ratings2]
-        if len(r1) < 3: return 0.0, len(r1), 0.0
-        r1, r2 = numpy.array(r1), numpy.array(r2)
-        similarity = r1.dot(r2) / (numpy.linalg.norm(r1) * numpy.linalg.norm(r2))
-        n = len(r1)
+        """(final_score, common_reviewers, pre_boost_score) of one pair (:72-119), used by
+        ``tune`` exactly as in the reference.  The common raters, their dot product and norms --
+        the part that touches the ratings -- come from the device (``mrb_cosim_pair``, exact
+        integer sums, the cosine in the reference's operation order); the scalar boost below is
+        the reference's own expression, textually, so that libm rounds it the same way."""
+        n, similarity = self._pair(movie_id1_index, movie_id2_index)
+        if n < 3: return 0.0, n, 0.0
         x_limit = 3 * math.exp(self.buff_limit)
         x = 3 + (x_limit - 3) * (n - 3) / (self.buff_point - 3)
         buff = math.log(x) - math.log(3)

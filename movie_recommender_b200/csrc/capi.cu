@@ -626,6 +626,14 @@ int mrb_cosim_query(mrb_cosim* h, int q_lo, int q_hi, const double* buff, int bu
     });
 }
 
+int mrb_cosim_pair(mrb_cosim* h, int a, int b, int* common_raters, double* similarity) {
+    return guarded([&] {
+        MRB_REQUIRE(h != nullptr && common_raters != nullptr && similarity != nullptr, "null argument");
+        h->impl.pair(a, b, common_raters, similarity);
+        return 0;
+    });
+}
+
 void mrb_cosim_destroy(mrb_cosim* h) { delete h; }
 
 int mrb_cosine_topk(const double* factors, int num_items, int num_factors, int topk, int q_lo,

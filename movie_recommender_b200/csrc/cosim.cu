@@ -247,6 +247,62 @@ Cosim::~Cosim() {
     if (s_) cudaStreamDestroy(s_);
 }
 
+namespace {
+// One pair (a, b): common raters n, D = sum q_a q_b, S_a = sum q_a^2, S_b = sum q_b^2 over them
+// (q = 2 * rating: small exact integers), then the cosine in the reference's operation order
+// (build_similar_movies_db.py:72-107).  For every rater u of a, u's movie list is scanned for b.
+__global__ void __launch_bounds__(256)
+k_cosim_pair(const int* __restrict__ m_ptr, const int* __restrict__ m_user, const unsigned char* __restrict__ m_rq,
+             const int* __restrict__ u_ptr, const int* __restrict__ u_movie, const unsigned char* __restrict__ u_rq,
+             int a, int b, int* __restrict__ n_out, double* __restrict__ sim_out) {
+    __shared__ unsigned long long acc[4];
+    if (threadIdx.x < 4) acc[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long n = 0, d = 0, sa = 0, sb = 0;
+    for (int e = m_ptr[a] + threadIdx.x; e < m_ptr[a + 1]; e += blockDim.x) {
+        const int u = m_user[e];
+        const unsigned long long ra = m_rq[e];
+        for (int f = u_ptr[u]; f < u_ptr[u + 1]; f++)
+            if (u_movie[f] == b) {
+                const unsigned long long rb = u_rq[f];
+                n++;
+                d += ra * rb;
+                sa += ra * ra;
+                sb += rb * rb;
+                break;
+            }
+    }
+    atomicAdd(&acc[0], n);
+    atomicAdd(&acc[1], d);
+    atomicAdd(&acc[2], sa);
+    atomicAdd(&acc[3], sb);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *n_out = static_cast<int>(acc[0]);
+        double sim = 0.0;
+        if (acc[0] >= 3) {
+            const double dot = static_cast<double>(acc[1]) * 0.25;
+            const double na = sqrt(static_cast<double>(acc[2]) * 0.25);
+            const double nb = sqrt(static_cast<double>(acc[3]) * 0.25);
+            sim = __ddiv_rn(dot, __dmul_rn(na, nb));                       // :107
+        }
+        *sim_out = sim;
+    }
+}
+}  // namespace
+
+void Cosim::pair(int a, int b, int* n_out, double* sim_out) {
+    MRB_REQUIRE(a >= 0 && a < N_ && b >= 0 && b < N_, "cosim: movie index out of range");
+    DevBuf<int> d_n(1);
+    DevBuf<double> d_sim(1);
+    k_cosim_pair<<<1, 256, 0, s_>>>(m_ptr_.p, m_user_.p, m_rq_.p, u_ptr_.p, u_movie_.p, u_rq_.p, a, b, d_n.p, d_sim.p);
+    MRB_LAUNCHED(1);
+    MRB_CUDA(cudaGetLastError());
+    d_n.download(n_out, 1, s_);
+    d_sim.download(sim_out, 1, s_);
+    MRB_CUDA(cudaStreamSynchronize(s_));
+}
+
 float Cosim::query(int q_lo, int q_hi, const double* buff, int buff_len, int num_results,
                    int* out_idx, double* out_score, int* out_count) {
     MRB_REQUIRE(q_lo >= 0 && q_lo <= q_hi && q_hi <= N_, "cosim: bad query range");

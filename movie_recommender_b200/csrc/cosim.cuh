@@ -22,6 +22,10 @@ public:
     float query(int q_lo, int q_hi, const double* buff, int buff_len, int num_results,
                 int* out_idx, double* out_score, int* out_count);
 
+    // One pair of movies (list indices): the number of common raters and the cosine of their
+    // ratings over them (0 when fewer than 3), as _scaled_dot_product computes them (:72-107).
+    void pair(int a, int b, int* n_out, double* sim_out);
+
 private:
     int N_, U_, ctas_ = 0;
     cudaStream_t s_ = nullptr;

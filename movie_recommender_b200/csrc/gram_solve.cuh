@@ -209,7 +209,8 @@ MRB_DEVICE_INLINE void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], int n,
         for (int tk = 0; tk < M8; tk++) {
             const int D = TI(tk, tk);
             // the 8 pivot columns, rolled in pairs (cp = c >> 1 at run time, slot j = c & 1 static):
-            // 4x less code than a full unroll -- the epilogue was instruction-cache bound
+            // 4x less code than a full unroll -- the epilogue was instruction-cache bound (a full
+            // unroll measured 9.78 vs 9.70 ms per C3 sweep, profiles/ab_unroll_r02.log)
     #pragma unroll 1
             for (int cp = 0; cp < 4; cp++) {
     #pragma unroll
@@ -398,19 +399,27 @@ MRB_DEVICE_INLINE void gram_solve(double (&acc)[M8 * (M8 + 1) / 2][2], int n,
         xq[tj][1] += dlt[1];
     }
     }
-    if (p == 0) {
+    // ---- store the solved row: lane-linear, so that one store instruction writes 32 consecutive
+    // doubles (full 32-byte sectors) -- into this GPU's replica and, fused all-gather, into every
+    // peer replica over NVLink.  (Round 1 stored from the four lanes that own the column layout:
+    // 14 half-filled sectors per replica and row; at N = 8 the 7 x 14 scattered 8-byte peer
+    // stores per row cost 15 % of the launch, profiles/share_times_r02.txt.)
+    // xq is replicated over p: lane l fetches element c = l + 32 h from the lane whose q owns it.
+    double lin[2] = {0.0, 0.0};
 #pragma unroll
-        for (int t = 0; t < M8; t++)
+    for (int t = 0; t < M8; t++)
 #pragma unroll
-            for (int s = 0; s < 2; s++) {
-                const int c = 8 * t + 2 * q + s;
-                if (c < n) {
-                    const double v = xq[t][s];
-                    xo[c] = v;
-                    // fused all-gather: the solved row goes into every peer replica as well
-                    for (int j = 0; j < A.n_peers; j++) A.x_peers[j][row_offset + c] = v;
-                }
-            }
+        for (int s = 0; s < 2; s++) {
+            const double v = shfl_double(xq[t][s], (lane & 7) >> 1);
+            if ((lane >> 3) == (t & 3) && (lane & 1) == s) lin[t >> 2] = v;
+        }
+#pragma unroll
+    for (int h = 0; h < (M8 > 4 ? 2 : 1); h++) {
+        const int c = lane + 32 * h;
+        if (c < n) {
+            xo[c] = lin[h];
+            for (int j = 0; j < A.n_peers; j++) A.x_peers[j][row_offset + c] = lin[h];
+        }
     }
 }
 

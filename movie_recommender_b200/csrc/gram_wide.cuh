@@ -78,7 +78,10 @@ __device__ __forceinline__ void wide_factor_diag(double& d0, double& d1, double&
                                                  double thr, int npiv, int lane, double* corner) {
     const int p = lane >> 2, q = lane & 3;
     double invd = 0;
-#pragma unroll 1
+    // fully unrolled: one copy of this code per kernel (the tile-column loop around it is rolled),
+    // and with c, cp static every lane predicate and shuffle source folds to a constant (79.8 vs
+    // 82.0 ms per k = 128 sweep against the rolled-in-pairs form, profiles/ab_unroll_r02.log)
+#pragma unroll
     for (int cp = 0; cp < 4; cp++) {
 #pragma unroll
         for (int j = 0; j < 2; j++) {
@@ -422,20 +425,16 @@ k_gram_wide(const GramArgs A, const double* __restrict__ zero_row) {
                     part[t2][0] = fma(l.x, dp, part[t2][0]);
                     part[t2][1] = fma(l.y, dp, part[t2][1]);
                 }
-                // x = x0 + delta for this tile row, column layout -> the lanes with p == 0 store
-                const double dl0 = shfl_double(dp, (2 * q) * 4), dl1 = shfl_double(dp, (2 * q + 1) * 4);
-                if (p == 0) {
-#pragma unroll
-                    for (int s = 0; s < 2; s++) {
-                        const int c = 8 * tj + 2 * q + s;
-                        if (c < n) {
-                            const double v = sm.x0[c] + (s ? dl1 : dl0);
-                            xo[c] = v;
-                            for (int j = 0; j < A.n_peers; j++)
-                                A.x_peers[j][static_cast<size_t>(wi.owner) * n + c] = v;
-                        }
-                    }
-                }
+                // x = x0 + delta for this tile row: delta[8 tj + p] is replicated over q
+                if (q == 0 && 8 * tj + p < n) sm.x0[8 * tj + p] += dp;
+            }
+            // the solved row, lane-linear: full 32-byte sectors into this GPU's replica and, fused
+            // all-gather, into every peer replica over NVLink
+            __syncwarp();
+            for (int c = lane; c < n; c += 32) {
+                const double v = sm.x0[c];
+                xo[c] = v;
+                for (int j = 0; j < A.n_peers; j++) A.x_peers[j][static_cast<size_t>(wi.owner) * n + c] = v;
             }
         }
     }

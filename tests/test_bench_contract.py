@@ -29,3 +29,26 @@ def test_metric_names_follow_baseline_json():
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     assert "ratings/sec per sweep" in base["metric"] and b.UNIT == "ratings/s"
     assert "per_sweep" in b.METRIC
+
+
+def test_algorithmic_flops_match_the_survey():
+    b = load_bench()
+    # F_u + F_i = 1.50e11, Cholesky 1.5e10 => 1.65e11 per sweep at C3
+    assert abs(b.algorithmic_flops_per_sweep(b.WORKLOAD) / 1e11 - 1.65) < 0.01
+
+
+def test_reference_sample_keeps_the_shrink_rule():
+    """The reference arm's subsample re-applies the reference's shrink rule: every movie keeps
+    >= k ratings and every user >= k + 1, ids are dense, the sample is a subset of the workload."""
+    import numpy as np
+    b = load_bench()
+    w = dict(b.WORKLOAD, name="dev", num_users=6000, num_items=900, num_ratings=500000, k=20)
+    p, _ = b.make_problem(w, 7)
+    s = b.shrunk_user_subsample(p, w, 0.5)
+    assert 0 < len(s["ratings"]) < len(p["ratings"])
+    cu = np.bincount(s["user_ids"], minlength=s["num_users"])
+    ci = np.bincount(s["item_ids"], minlength=s["num_items"])
+    assert cu.min() >= w["k"] + 1 and ci.min() >= w["k"]
+    assert s["user_ids"].max() == s["num_users"] - 1 and s["item_ids"].max() == s["num_items"] - 1
+    assert len(s["user_factors0"]) == s["num_users"] * (w["k"] + 1)
+    assert "shrink rule" in b.sample_description(s, w)

@@ -72,3 +72,42 @@ def test_edge_cases(require_gpu):
     # off-grid ratings are refused (the kernel's exact integer accumulation needs the 0.5 grid)
     with pytest.raises(ValueError):
         F({1: {0}}, [(1, {10: 3.3})])
+
+
+def test_pair_score_is_computed_on_the_device(require_gpu):
+    """tune()'s pair score (build_similar_movies_db.py:72-119): common raters and cosine from
+    mrb_cosim_pair, bit-equal to the NumPy expression the reference evaluates, for every pair of
+    a catalogue whose rater lists are NOT sorted by user id."""
+    import math
+    genres, ratings = synthetic_catalogue(num_movies=40, num_users=90, density=0.35, seed=5)
+    rng = np.random.default_rng(0)
+    shuffled = []
+    for mid, d in ratings:
+        users = list(d)
+        rng.shuffle(users)
+        shuffled.append((mid, {u: d[u] for u in users}))
+    f = finder_cls()(genres, shuffled, buff_limit=0.3, buff_point=12)
+    seen_boost = False
+    for a in range(len(shuffled)):
+        for b in range(len(shuffled)):
+            ra, rb = shuffled[a][1], shuffled[b][1]
+            if len(ra) > len(rb):
+                ra, rb = rb, ra
+            common = [u for u in ra if u in rb]
+            score, n, sim = f._scaled_dot_product(a, b)
+            assert n == len(common)
+            if n < 3:
+                assert (score, sim) == (0.0, 0.0)
+                continue
+            r1 = np.array([ra[u] for u in common])
+            r2 = np.array([rb[u] for u in common])
+            want = r1.dot(r2) / (np.linalg.norm(r1) * np.linalg.norm(r2))
+            assert float(sim).hex() == float(want).hex(), (a, b)
+            x = 3 + (3 * math.exp(0.3) - 3) * (n - 3) / (12 - 3)
+            buff = min(max(math.log(x) - math.log(3), 0), 0.3)
+            assert float(score).hex() == float(want * (1.0 + buff)).hex()
+            seen_boost |= buff > 0
+    assert seen_boost
+    with pytest.raises(Exception):
+        f._pair(0, len(shuffled))
+    f.close()

@@ -1,7 +1,7 @@
 """Host logic of the SimilarMovieFinder mirror (movie_recommender_b200/build_similar_movies_db.py)
 on CPU: marshalling of the reference's list-of-dicts input, the buff table, find_similar_movie /
-build / tune around the device query.  The device query itself (`mrb_cosim_create` +
-`_query`) is replaced by the oracle restatement here (the real one is exercised by
+build / tune around the device calls.  The device calls themselves (`mrb_cosim_create`, `_query`,
+`_pair`) are replaced by the oracle restatement here (the real one is exercised by
 tests/test_gpu_cosim.py); the expectation is the golden output of the REAL reference class."""
 import json
 import math
@@ -42,7 +42,17 @@ def Finder(monkeypatch):
                 score[q, j] = s
         return idx, score, count
 
+    def fake_pair(self, a, b):
+        # build_similar_movies_db.py:72-107 restated: cosine over the common raters
+        ra, rb = self.movie_ratings[a][1], self.movie_ratings[b][1]
+        common = [u for u in ra if u in rb]
+        if len(common) < 3:
+            return len(common), 0.0
+        r1, r2 = np.array([ra[u] for u in common]), np.array([rb[u] for u in common])
+        return len(common), float(r1.dot(r2) / (np.linalg.norm(r1) * np.linalg.norm(r2)))
+
     monkeypatch.setattr(mod._dll, "mrb_cosim_create", fake_create)
+    monkeypatch.setattr(mod.SimilarMovieFinder, "_pair", fake_pair)
     monkeypatch.setattr(mod.SimilarMovieFinder, "_query", fake_query)
     mod.SimilarMovieFinder._captured = captured
     return mod.SimilarMovieFinder
