@@ -66,8 +66,8 @@ FP64_DMMA_PEAK_FALLBACK_TFLOPS = 37.09
 # dram__bytes_read.sum + dram__bytes_write.sum of the two k_gram launches of one sweep at C3 from
 # the committed ncu --set full capture named in NCU_TRAFFIC_SOURCE: far BELOW the algorithmic
 # gather bytes because the factor rows are served by L2.
-NCU_DRAM_BYTES_PER_LAUNCH_C3 = (0.558801e9 + 0.115597e9 + 4.056275e9 + 0.114527e9) / 2.0
-NCU_TRAFFIC_SOURCE = "profiles/ncu_k_gram_C3_r01_v4.txt (1 GPU capture)"
+NCU_DRAM_BYTES_PER_LAUNCH_C3 = (0.557734e9 + 0.115908e9 + 3.967396e9 + 0.114395e9) / 2.0
+NCU_TRAFFIC_SOURCE = "profiles/ncu_k_gram_C3_r02.txt (1 GPU capture of this round's kernel)"
 
 
 def load_peaks():
