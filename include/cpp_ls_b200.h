@@ -254,8 +254,10 @@ MRB_API int mrb_cosine_topk(const double* factors, int num_items, int num_factor
  *    (python/full_data/build_similar_movies_db.py:21-221: genre gate :44-69, cosine over the
  *    common raters with the log "buff" :72-119, reliability cut and top-k :151-180), bit-exact.
  *    Inputs are two CSR views of the same ratings (by movie list index and by user), ratings as
- *    rq = 2*rating (0.5 grid, rq <= 20), a genre bit mask and genre count per movie (count 0 =
- *    no genre entry), and buff[n] tabulated by the host with the reference's libm calls.
+ *    rq = 2*rating (0.5 grid, rq <= 20), a genre bit mask and genre count per movie (count =
+ *    number of bits set; 0 = no genre entry), and buff[n] tabulated by the host with the
+ *    reference's libm calls.  Every user's movie list must be strictly ascending (checked);
+ *    fewer than 2^24 movies and 2^27 users.
  * ---------------------------------------------------------------------------------------- */
 typedef struct mrb_cosim mrb_cosim;
 MRB_API int mrb_cosim_create(int num_movies, int num_users, const int* m_ptr, const int* m_user,

@@ -101,6 +101,8 @@ class SimilarMovieFinder:
             g = self.movie_genres.get(mid)
             if not g:
                 continue
+            if len(set(g)) != len(g):
+                raise ValueError("genres of movie %r hold duplicates (the reference takes sets)" % (mid,))
             m = 0
             for gid in g:
                 if gid not in genre_bit:

@@ -1,12 +1,15 @@
 // K6: the reference's co-rating similarity (SimilarMovieFinder) on the GPU (see cosim.cu).
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace mrb {
 
 class Cosim {
 public:
-    // Host CSR views of the same ratings: by movie (raters) and by user (movies); rq = 2*rating
+    // Host CSR views of the same ratings: by movie (raters) and by user (movies, strictly
+    // ascending within a user -- checked); rq = 2*rating
     // (ratings on the 0.5 grid, 0 <= rq <= 20); genre bit masks and genre counts per movie
     // (count 0 = the movie has no genre entry).
     Cosim(int num_movies, int num_users, const int* m_ptr, const int* m_user,
@@ -27,11 +30,14 @@ public:
     void pair(int a, int b, int* n_out, double* sim_out);
 
 private:
-    int N_, U_, ctas_ = 0;
+    int N_, U_, ctas_ = 0, parts_ = 1, part_movies_ = 32, smem_bytes_ = 0;
     cudaStream_t s_ = nullptr;
-    DevBuf<int> m_ptr_, m_user_, u_ptr_, u_movie_, gcnt_, cand_b_, cand_n_, counter_;
+    std::vector<int> order_all_;   // movies by number of raters, descending
+    std::vector<int> deg_;         // raters per movie
+    DevBuf<int> m_ptr_, m_user_, u_ptr_, u_movie_, gcnt_, cand_b_, cand_n_, counter_, split_;
     DevBuf<unsigned char> m_rq_, u_rq_;
-    DevBuf<unsigned long long> gmask_, scratch_;
+    DevBuf<unsigned long long> gmask_;
+    DevBuf<unsigned> m_pack_, u_pack_;   // id | rq << 27: what the query kernel streams
     DevBuf<double> cand_s_;
 };
 

@@ -244,7 +244,9 @@ def bench_a8(args, sampler):
     deg = np.bincount(u, minlength=nu).astype(np.float64)
     triples = float((deg ** 2).sum())
     hbm, _, src = _peaks()
-    # algorithmic bytes: one 16-byte packed accumulation per (query, rater, co-rated movie) triple
+    # algorithmic bytes: 16 bytes of accumulator update per (query, rater, co-rated movie) triple
+    # (SURVEY 8d's figure; since round 2 the accumulators live in shared memory, so this is an
+    # equivalent rate, not DRAM traffic -- DRAM sees the 4-byte packed list entries only)
     ach = triples * 16 / (ms * 1e-3) / 1e9
     out = {"metric": "similarities_per_sec", "value": ni * (ni - 1) / (ms * 1e-3), "unit": "pairs/s",
            "ms_per_step": ms, "dtype": "int64 accumulation + f64 scores",
@@ -256,10 +258,14 @@ def bench_a8(args, sampler):
                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": ni * 20 * 12,
                    "call": "SimilarMovieFinder.build() -> {movie id: similar ids} on the host (ratings uploaded "
                            "once at construction, setup_s)"},
-           "roofline": {"bound": "hbm", "kernel": "k_cosim (scattered packed-integer atomics)", "achieved": ach,
+           "roofline": {"bound": "hbm", "kernel": "k_cosim (shared-memory integer atomics, 4 x u32 per movie, catalogue in 216 KB parts)", "achieved": ach,
                         "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": src,
-                        "note": "16 algorithmic bytes per co-rating triple; the kernel is bound by L2 atomic "
-                                "latency, not bandwidth"},
+                        "triples_per_cycle_per_sm": triples / (ms * 1e-3) / 1.965e9 / 148,
+                        "note": "16 algorithmic bytes per co-rating triple; accumulators in shared memory "
+                                "(native ATOMS.ADD), so the bound is shared-memory atomic issue and the latency "
+                                "of the list gathers, not HBM: a heavy query alone runs at 1.2-1.3 triples per "
+                                "cycle and SM, the light two thirds of the queries are latency bound "
+                                "(profiles/cosim_query_times_r02.txt)"},
            "cpu_baseline": {"value": 25.9 * (ni - 1), "unit": "pairs/s", "cores": 16, "kind": "reference",
                             "sample": "published by the reference (BASELINE.md): 25.9 movies/s on m5.4xlarge, "
                                       "not re-timed here (pure-Python O(N^2 deg) loop)"}}
