@@ -44,6 +44,12 @@ constexpr int GRAM_WARPS = 4;      // warps per CTA
 // (Measured and rejected, profiles/ab_solve_r02.log: one CTA of 8 warps per SM whose two warps
 // per scheduler pass a "tensor token", so that one accumulates while the other solves -- a single
 // warp reaches only 64 % of the accumulation rate two warps reach together: 7.8 vs 6.6 ms.)
+// (Measured and rejected as well, profiles/ab_pair_r02.log: the two warps of a scheduler meeting
+// at a named barrier after their accumulation so that both accumulate and both solve at the same
+// time -- 10.7 vs 9.67 ms.  The solve is NOT slowed by the neighbour's DMMA stream: with the
+// accumulation switched off (MRB_DEBUG_SKIP_SOLVE=4) the user-side solves alone take 2.69 ms,
+// accumulation alone 3.37 ms, together 5.91 ms.  It is an in-order chain of ~3.7 k instructions
+// at ~5.6 cycles each; profiles/lat_fp64_r02.txt has the instruction latencies.)
 template <bool USER>
 constexpr int gram_warps() { return GRAM_WARPS; }
 #ifndef GRAM_RING_USER
@@ -162,7 +168,7 @@ k_gram(const GramArgs A) {
         // Fragments are fetched TWO k-steps ahead of their use (f -> f1 -> f2), ids/ratings a
         // whole 32-rating batch ahead, so that an HBM miss (user factors do not fit L2 entirely)
         // has ~2 x 28 DMMA issue times to land.
-        const int cnt = wi.end - wi.beg;
+        const int cnt = (A.debug_skip_solve & 4) ? 0 : wi.end - wi.beg;   // 4 = measurement only: the solve alone
         const int nsteps = (cnt + 3) >> 2;
         int ids_cur = 0, ids_nxt = 0;
         double rts_cur = 0, rts_nxt = 0;

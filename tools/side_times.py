@@ -42,4 +42,6 @@ info = prob.run(4, -1e300, 10)
 out["sweep_ms"] = info.device_ms / 10
 os.environ["MRB_DEBUG_SKIP_SOLVE"] = "1"
 out["user_accumulate_only_ms"], out["item_accumulate_only_ms"] = side(True), side(False)
+os.environ["MRB_DEBUG_SKIP_SOLVE"] = "4"
+out["user_solve_only_ms"], out["item_solve_only_ms"] = side(True), side(False)
 print(" ".join("%s=%.3f" % kv for kv in out.items()), "setup %.1fs" % (time.time() - t))
