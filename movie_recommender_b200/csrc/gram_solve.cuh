@@ -115,6 +115,12 @@ MRB_DEVICE_INLINE double xor_sum_q(double v) {   // sum over the 4 lanes sharing
 // VARIANT 3: additionally the panel below the diagonal tile stays out of the pivot loop and is
 //   formed afterwards as X W on the tensor cores (2 DMMA per tile, operands without shuffles via
 //   the even/odd column split, W^T by one fragment transpose).
+// (Measured and rejected, profiles/ab_v4_r02.log, ab_v5_r02.log: broadcasting the pivot first and
+//  forming 1/d on every lane (MUFU.RCP64H + 3 fp64 operations instead of rsqrt + square on the
+//  chain) shortens the solves ALONE from 2.69 to 2.53 ms but lengthens the half-sweep, 5.91 ->
+//  6.09 ms: next to a warp that streams DMMAs every additional fp64 instruction waits for the
+//  shared pipe; computing the eight reciprocal square roots of a tile column together afterwards
+//  did not help either, 5.97 ms.)
 // (A block-of-four pivot variant was measured and rejected: 7.25 vs 6.63 ms on the user side of
 //  C3, profiles/ab_b4_r02.log.)
 template <int M8, int VARIANT = 0>
