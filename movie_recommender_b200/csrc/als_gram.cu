@@ -50,6 +50,9 @@ constexpr int GRAM_WARPS = 4;      // warps per CTA
 // accumulation switched off (MRB_DEBUG_SKIP_SOLVE=4) the user-side solves alone take 2.69 ms,
 // accumulation alone 3.37 ms, together 5.91 ms.  It is an in-order chain of ~3.7 k instructions
 // at ~5.6 cycles each; profiles/lat_fp64_r02.txt has the instruction latencies.)
+// (CTA shapes other than 4 warps leave schedulers unevenly loaded -- warp w of a CTA runs on
+// scheduler w mod 4: 3 CTAs x 3 warps at 224 registers 12.3 ms, 2 x 5 warps at 200 registers
+// 16.4 ms per sweep, profiles/ab_shape_r02.log.)
 template <bool USER>
 constexpr int gram_warps() { return GRAM_WARPS; }
 #ifndef GRAM_RING_USER
