@@ -63,8 +63,7 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
     ratings_.alloc(nnz);
     u_ptr_.alloc(static_cast<size_t>(nu_) + 1);
     i_ptr_.alloc(static_cast<size_t>(ni_) + 1);
-    u_idx_.alloc(nnz);
-    i_idx_.alloc(nnz);
+    // (u_idx_ / i_idx_ are allocated by build_index: a dealt multi-GPU rank never needs them)
     uf_.alloc(static_cast<size_t>(nu_) * (k + 1));
     itf_.alloc(static_cast<size_t>(ni_) * k);
     // The ids go first on the compute stream; the ratings (half of the bytes, not needed by
@@ -107,11 +106,11 @@ void AlsProblem::push_coo_slice() {
     MRB_CUDA(cudaStreamWaitEvent(s_, ev_ratings_, 0));
 }
 
-void AlsProblem::build_index() {
-    if (index_built_) return;
+// ids must be zero based and inside the factor arrays (python/full_data/cpp_ls.py:120-123); the
+// reference would read out of bounds, we refuse.
+void AlsProblem::check_ids() {
+    if (ids_checked_) return;
     const int nnz = nnz_;
-    // ids must be zero based and inside the factor arrays (python/full_data/cpp_ls.py:120-123);
-    // the reference would read out of bounds, we refuse.
     DevBuf<int> bad(1);
     MRB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s_));
     if (nnz > 0) {
@@ -125,7 +124,15 @@ void AlsProblem::build_index() {
         cudaStreamSynchronize(s_copy_);
         MRB_REQUIRE(false, "als: user/item id outside [0, num_users/num_items)");
     }
+    ids_checked_ = true;
+}
 
+void AlsProblem::build_index() {
+    if (index_built_) return;
+    const int nnz = nnz_;
+    check_ids();
+    if (u_idx_.n != static_cast<size_t>(nnz)) u_idx_.alloc(nnz);
+    if (i_idx_.n != static_cast<size_t>(nnz)) i_idx_.alloc(nnz);
     PhaseTimer t_idx("  index build (2 group_by)");
     EventPair ev;
     MRB_CUDA(cudaEventRecord(ev.e0, s_));
@@ -135,6 +142,18 @@ void AlsProblem::build_index() {
     MRB_CUDA(cudaEventSynchronize(ev.e1));
     MRB_CUDA(cudaEventElapsedTime(&index_ms_, ev.e0, ev.e1));
     index_built_ = true;
+    pointers_built_ = true;
+}
+
+// The row pointers alone (degree histograms + scans): all a rank of a dealt multi-GPU run needs
+// of the other ranks' rows -- it groups only the ratings of the rows it owns (als_gram.cu).
+void AlsProblem::build_pointers() {
+    if (pointers_built_) return;
+    check_ids();
+    PhaseTimer t_idx("  row pointers (2 histograms)");
+    group_pointers(user_ids_.p, nnz_, nu_, u_ptr_.p, s_);
+    group_pointers(item_ids_.p, nnz_, ni_, i_ptr_.p, s_);
+    pointers_built_ = true;
 }
 
 void AlsProblem::destroy_handles() {

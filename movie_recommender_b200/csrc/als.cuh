@@ -49,6 +49,7 @@ public:
                int num_users, int num_items, int slice_begin = 0, int slice_len = -1);
     ~AlsProblem();
     void build_index();                      // id check + the two stable groupings
+    void build_pointers();                   // id check + the row pointers only (dealt multi-GPU ranks)
     // peer replicas of the three COO arrays, index = rank (own entry ignored)
     void set_coo_peers(const std::vector<int*>& user_ids, const std::vector<int*>& item_ids,
                        const std::vector<double*>& ratings);
@@ -124,6 +125,7 @@ private:
     void wait_factors();   // s_ waits for a pending set_factors_async
     void launch_half(bool user_side, cudaStream_t stream, int epilogue);
     void destroy_handles();
+    void check_ids();
 
     int nnz_, k_, nu_, ni_;
     cudaStream_t s_ = nullptr, s_copy_ = nullptr;
@@ -138,7 +140,7 @@ private:
     float index_ms_ = 0;
     int rank_ = 0, world_ = 1, partition_ = 0;
     int slice_begin_ = 0, slice_len_ = -1;
-    bool index_built_ = false;
+    bool index_built_ = false, pointers_built_ = false, ids_checked_ = false;
     std::vector<int*> uid_peers_, iid_peers_;
     std::vector<double*> rating_peers_;
     std::vector<double*> uf_peers_, itf_peers_;

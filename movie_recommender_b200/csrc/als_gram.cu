@@ -624,6 +624,12 @@ struct Side {
     int lo = 0, hi = 0;   // owner range of this rank
     DevBuf<int> owner_order;   // owners with ratings, longest first (wide-rank path)
     int n_owner_items = 0;
+    // where owner o's ratings sit in other_g / rating_g: the CSR pointers of the full grouping,
+    // or (owned-rows mode) cptr, the exclusive scan of the degrees of this rank's owners -- the
+    // grouped copies then hold this rank's rows only
+    const int* gptr = nullptr;
+    DevBuf<int> cptr;
+    int n_grouped = 0;         // entries of other_g / rating_g
 };
 
 // Grouped copies of the opposite-side ids and the ratings (what k_gram streams through).
@@ -637,6 +643,59 @@ void build_side_gather(Side& sd, const int* d_idx, const int* d_other_ids, const
         MRB_LAUNCHED(1);
     }
     MRB_CUDA(cudaGetLastError());
+}
+
+// Owned-rows mode (rows dealt over several GPUs): the grouped copies of THIS RANK'S rows only.
+// The ratings whose row is owned are compacted in input order, sorted by row with the stable
+// radix sort, and gathered: row o's ratings land at cptr[o] .. cptr[o+1] in the order the full
+// stable grouping would give them -- the bits of the solve do not depend on the number of GPUs.
+__global__ void k_owned_flags(const int* __restrict__ key, int nnz, const int* __restrict__ cptr,
+                              int* __restrict__ flag) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const int o = key[e];
+    flag[e] = cptr[o + 1] > cptr[o] ? 1 : 0;
+}
+
+__global__ void k_compact_owned(const int* __restrict__ key, int nnz, const int* __restrict__ cptr,
+                                const int* __restrict__ pos, int* __restrict__ ckey, int* __restrict__ cval) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const int o = key[e];
+    if (cptr[o + 1] > cptr[o]) {
+        ckey[pos[e]] = o;
+        cval[pos[e]] = e;
+    }
+}
+
+void build_side_gather_owned(Side& sd, const int* d_key, const int* d_other_ids, const double* d_ratings,
+                             int nnz, int owners, cudaStream_t s) {
+    const int m = sd.n_grouped;
+    sd.other_g.alloc(std::max(m, 1));
+    sd.rating_g.alloc(std::max(m, 1));
+    if (m == 0 || nnz == 0) return;
+    DevBuf<int> pos(nnz), ckey(m), cval(m), skey(m), sval(m);
+    k_owned_flags<<<ceil_div(nnz, 256), 256, 0, s>>>(d_key, nnz, sd.cptr.p, pos.p); MRB_LAUNCHED(1);
+    exclusive_scan_i32(pos.p, pos.p, nnz, s);
+    k_compact_owned<<<ceil_div(nnz, 256), 256, 0, s>>>(d_key, nnz, sd.cptr.p, pos.p, ckey.p, cval.p);
+    MRB_LAUNCHED(1);
+    int bits = 0;
+    while (bits < 31 && (1LL << bits) < owners) bits++;
+    const unsigned mask = (1u << ((bits + 7) / 8)) - 1u;
+    stable_sort_pairs(ckey.p, cval.p, m, mask, skey.p, sval.p, s);   // synchronises s
+    k_gather_grouped<<<ceil_div(m, 256), 256, 0, s>>>(sval.p, d_other_ids, d_ratings, m, sd.other_g.p,
+                                                     sd.rating_g.p);
+    MRB_LAUNCHED(1);
+    MRB_CUDA(cudaGetLastError());
+    MRB_CUDA(cudaStreamSynchronize(s));   // the scratch buffers are released on return
+}
+
+__global__ void k_mark_owned(const int* __restrict__ ptr, const int* __restrict__ mine, int m,
+                             int* __restrict__ owned_deg) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    const int o = mine[t];
+    owned_deg[o] = ptr[o + 1] - ptr[o];
 }
 
 // ---- work lists, built on the device --------------------------------------------------------
@@ -726,11 +785,20 @@ int dealt_count(int owners, int rank, int world) {
 // when the rows are sharded in contiguous ranges (the balanced ranges are a host decision every
 // rank must agree on), and four totals.
 void build_side_lists(Side& sd, const int* d_ptr, int owners, int nnz, int rank, int world,
-                      int partition, cudaStream_t s) {
+                      int partition, bool owned_only, cudaStream_t s) {
     PhaseTimer t2("  side: work lists");
     sd.lo = 0;
     sd.hi = owners;
+    sd.gptr = d_ptr;
+    sd.n_grouped = nnz;
     const bool dealt = world > 1 && partition == 1;
+    MRB_REQUIRE(!owned_only || dealt, "als: owned-rows grouping needs the dealt partition");
+    if (owned_only) {
+        sd.cptr.alloc(static_cast<size_t>(owners) + 1);
+        MRB_CUDA(cudaMemsetAsync(sd.cptr.p, 0, sizeof(int) * (static_cast<size_t>(owners) + 1), s));
+        sd.gptr = sd.cptr.p;
+        sd.n_grouped = 0;
+    }
     if (world > 1 && !dealt) {
         std::vector<int> ptr(static_cast<size_t>(owners) + 1);
         MRB_CUDA(cudaMemcpyAsync(ptr.data(), d_ptr, sizeof(int) * ptr.size(), cudaMemcpyDeviceToHost, s));
@@ -746,7 +814,7 @@ void build_side_lists(Side& sd, const int* d_ptr, int owners, int nnz, int rank,
     sd.owner_order.alloc(static_cast<size_t>(std::max(m, 1)));
     // every owner has at most deg / GRAM_SEG + 1 items
     sd.work.alloc(static_cast<size_t>(m) + static_cast<size_t>(nnz) / GRAM_SEG + 1);
-    if (m == 0) return;
+    if (m == 0) return;   // (owned-rows mode: cptr is all zero, nothing is grouped)
     DevBuf<int> key(m_all), kptr(LPT_KEYS + 1), order(m_all), mine;
     DevBuf<int> counts(4 * (static_cast<size_t>(m) + 1));
     int* item_at = counts.p;
@@ -763,22 +831,30 @@ void build_side_lists(Side& sd, const int* d_ptr, int owners, int nnz, int rank,
         MRB_LAUNCHED(1);
         my_order = mine.p;
     }
-    k_owner_counts<<<ceil_div(m + 1, 256), 256, 0, s>>>(d_ptr, sd.lo, m, my_order, item_at, multi_at,
+    if (owned_only) {
+        k_mark_owned<<<ceil_div(m, 256), 256, 0, s>>>(d_ptr, mine.p, m, sd.cptr.p); MRB_LAUNCHED(1);
+        exclusive_scan_i32(sd.cptr.p, sd.cptr.p, static_cast<long long>(owners) + 1, s);
+    }
+    const int* gptr = sd.gptr;
+    k_owner_counts<<<ceil_div(m + 1, 256), 256, 0, s>>>(gptr, sd.lo, m, my_order, item_at, multi_at,
                                                        slot_at, nonempty_at);
     MRB_LAUNCHED(1);
     exclusive_scan_i32(item_at, item_at, m + 1, s);
     exclusive_scan_i32(multi_at, multi_at, m + 1, s);
     exclusive_scan_i32(slot_at, slot_at, m + 1, s);
     exclusive_scan_i32(nonempty_at, nonempty_at, m + 1, s);
-    k_write_work<<<ceil_div(m, 256), 256, 0, s>>>(d_ptr, sd.lo, m, my_order, item_at, multi_at,
+    k_write_work<<<ceil_div(m, 256), 256, 0, s>>>(gptr, sd.lo, m, my_order, item_at, multi_at,
                                                  slot_at, nonempty_at, sd.work.p, sd.owner_order.p);
     MRB_LAUNCHED(1);
     MRB_CUDA(cudaGetLastError());
-    int totals[4] = {0, 0, 0, 0};
+    int totals[4] = {0, 0, 0, 0}, grouped = nnz;
     for (int t = 0; t < 4; t++)
         MRB_CUDA(cudaMemcpyAsync(&totals[t], counts.p + static_cast<size_t>(t) * (m + 1) + m,
                                  sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (owned_only)
+        MRB_CUDA(cudaMemcpyAsync(&grouped, sd.cptr.p + owners, sizeof(int), cudaMemcpyDeviceToHost, s));
     MRB_CUDA(cudaStreamSynchronize(s));   // also: the scratch buffers are released on return
+    sd.n_grouped = grouped;
     sd.n_work = totals[0];
     sd.n_multi = totals[1];
     sd.n_slots = totals[2];
@@ -944,18 +1020,26 @@ void AlsProblem::ensure_gram() {
     MRB_REQUIRE(n_u <= 160, "als algorithm 3/4: rank above 159 is not supported");
     if (gram_ && gram_->built_rank == rank_ && gram_->built_world == world_ &&
         gram_->built_partition == partition_) return;
-    build_index();
+    // rows dealt over several GPUs: only the rows this rank owns are grouped (1/world of the
+    // sorting work and of the grouped copies); the row pointers of all rows come from histograms
+    const bool owned_only = world_ > 1 && partition_ == 1 && std::getenv("MRB_FULL_INDEX") == nullptr;
+    if (owned_only) build_pointers(); else build_index();
     PhaseTimer t_g("ensure_gram (work lists)");
     gram_ = std::make_shared<GramState>();
     GramState& g = *gram_;
     int dev = 0;
     MRB_CUDA(cudaGetDevice(&dev));
     MRB_CUDA(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, dev));
-    build_side_lists(g.user, u_ptr_.p, nu_, nnz_, rank_, world_, partition_, s_);
-    build_side_lists(g.item, i_ptr_.p, ni_, nnz_, rank_, world_, partition_, s_);
+    build_side_lists(g.user, u_ptr_.p, nu_, nnz_, rank_, world_, partition_, owned_only, s_);
+    build_side_lists(g.item, i_ptr_.p, ni_, nnz_, rank_, world_, partition_, owned_only, s_);
     wait_ratings();
-    build_side_gather(g.user, u_idx_.p, item_ids_.p, ratings_.p, nnz_, s_);
-    build_side_gather(g.item, i_idx_.p, user_ids_.p, ratings_.p, nnz_, s_);
+    if (owned_only) {
+        build_side_gather_owned(g.user, user_ids_.p, item_ids_.p, ratings_.p, nnz_, nu_, s_);
+        build_side_gather_owned(g.item, item_ids_.p, user_ids_.p, ratings_.p, nnz_, ni_, s_);
+    } else {
+        build_side_gather(g.user, u_idx_.p, item_ids_.p, ratings_.p, nnz_, s_);
+        build_side_gather(g.item, i_idx_.p, user_ids_.p, ratings_.p, nnz_, s_);
+    }
     MRB_CUDA(cudaEventRecord(ev_prepared_, s_));
     prepared_recorded_ = true;
     g.wide = m8 > 7;
@@ -1039,7 +1123,7 @@ void AlsProblem::launch_half(bool user_side, cudaStream_t stream, int epilogue) 
                     a.block_c0[a.n_blocks] = c0;
                     a.n_blocks++;
                 }
-        a.ptr = user_side ? u_ptr_.p : i_ptr_.p;
+        a.ptr = sd.gptr;
         a.work_counter = g.counters.p;
         a.other_g = sd.other_g.p;
         a.rating_g = sd.rating_g.p;

@@ -293,6 +293,7 @@ int mrb_als_get_index(mrb_als_problem* p, int* u_ptr, int* u_idx, int* i_ptr, in
     return guarded([&] {
         MRB_REQUIRE(p != nullptr, "null problem");
         AlsProblem& a = p->impl;
+        a.build_index();   // a dealt multi-GPU rank has the row pointers only until asked
         cudaStream_t s = a.stream();
         const size_t nnz = static_cast<size_t>(a.nnz());
         MRB_CUDA(cudaMemcpyAsync(u_ptr, a.u_ptr(), sizeof(int) * (a.num_users() + 1ull), cudaMemcpyDeviceToHost, s));
@@ -463,8 +464,10 @@ int mrb_als_push_coo(mrb_als_problem* p) {
 int mrb_als_build_index(mrb_als_problem* p) {
     return guarded([&] {
         MRB_REQUIRE(p != nullptr, "null problem");
-        p->impl.build_index();
-        p->impl.half_sweep_prepare();   // this rank's work lists
+        // this rank's work lists; the index they need is built on the way: both groupings in
+        // full, or -- rows dealt over several GPUs -- the row pointers plus the grouping of the
+        // rows this rank owns
+        p->impl.half_sweep_prepare();
         return 0;
     });
 }

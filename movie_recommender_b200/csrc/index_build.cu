@@ -186,6 +186,16 @@ __global__ void k_iota(int* __restrict__ out, int n) {
 }
 }  // namespace
 
+void group_pointers(const int* d_key, int n, int num_groups, int* d_ptr, cudaStream_t s) {
+    MRB_REQUIRE(n >= 0 && num_groups >= 0, "group_pointers: negative size");
+    MRB_CUDA(cudaMemsetAsync(d_ptr, 0, sizeof(int) * (static_cast<size_t>(num_groups) + 1), s));
+    if (n == 0) return;
+    MRB_REQUIRE(num_groups > 0, "group_pointers: items but no groups");
+    k_count_keys<<<ceil_div(n, 256), 256, 0, s>>>(d_key, n, d_ptr); MRB_LAUNCHED(1);
+    MRB_CUDA(cudaGetLastError());
+    exclusive_scan_i32(d_ptr, d_ptr, static_cast<long long>(num_groups) + 1, s);
+}
+
 void stable_group_by(const int* d_key, int n, int num_groups, int* d_ptr, int* d_idx,
                      cudaStream_t s) {
     MRB_REQUIRE(n >= 0 && num_groups >= 0, "stable_group_by: negative size");

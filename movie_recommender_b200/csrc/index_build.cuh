@@ -15,6 +15,9 @@ void exclusive_scan_i32(const int* d_in, int* d_out, long long n, cudaStream_t s
 void stable_group_by(const int* d_key, int n, int num_groups, int* d_ptr, int* d_idx,
                      cudaStream_t s);
 
+// The pointer array of stable_group_by alone: d_ptr[g] = number of keys below g.
+void group_pointers(const int* d_key, int n, int num_groups, int* d_ptr, cudaStream_t s);
+
 // Stable LSD radix sort of (key, value) pairs on selected 8-bit digits of the 32-bit key: bit d
 // of digit_mask selects bits 8d..8d+7 (unselected digits are ignored, e.g. because every key
 // carries the same value there).  d_val_in == nullptr means value i = i.  Outputs must not
