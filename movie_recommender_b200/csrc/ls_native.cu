@@ -24,6 +24,10 @@ namespace mrb {
 
 namespace {
 
+// UNIT: every stored value is exactly 1.0 (the indicator matrices of the bias model, config 2):
+// found once at upload (k_all_ones), the value streams are then not read at all -- 1.0 * x is x
+// bit for bit, so the results do not change.
+template <bool UNIT>
 __global__ void __launch_bounds__(256)
 k_csr_mul_thread(const int* __restrict__ rowptr, const int* __restrict__ colidx,
                  const double* __restrict__ vals, const double* __restrict__ x,
@@ -33,10 +37,16 @@ k_csr_mul_thread(const int* __restrict__ rowptr, const int* __restrict__ colidx,
     if (r >= rows) return;
     double s = 0;
     const int end = rowptr[r + 1];
-    for (int e = rowptr[r]; e < end; e++) s += vals[e] * x[colidx[e]];
+    for (int e = rowptr[r]; e < end; e++) s += UNIT ? x[colidx[e]] : vals[e] * x[colidx[e]];
     y[r] = s;
 }
 
+__global__ void k_all_ones(const double* __restrict__ vals, int n, int* __restrict__ not_one) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && vals[i] != 1.0) *not_one = 1;
+}
+
+template <bool UNIT>
 __global__ void __launch_bounds__(256)
 k_csr_mul_warp(const int* __restrict__ rowptr, const int* __restrict__ colidx,
                const double* __restrict__ vals, const double* __restrict__ x,
@@ -47,7 +57,7 @@ k_csr_mul_warp(const int* __restrict__ rowptr, const int* __restrict__ colidx,
     const int lane = threadIdx.x & 31;
     double s = 0;
     const int end = rowptr[r + 1];
-    for (int e = rowptr[r] + lane; e < end; e += 32) s += vals[e] * x[colidx[e]];
+    for (int e = rowptr[r] + lane; e < end; e += 32) s += UNIT ? x[colidx[e]] : vals[e] * x[colidx[e]];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (lane == 0) y[r] = s;
@@ -117,7 +127,7 @@ __global__ void k_flat_col_ptr(const int* __restrict__ t_ptr, int cols,
     col_piece_ptr[c] = win_first[w] + __popc(heads[w] & ((1u << b) - 1u));
 }
 
-template <int WPW>   // windows per warp: all index/value loads, then all gathers, then the scans
+template <int WPW, bool UNIT>   // windows per warp: all index/value loads, then all gathers, then the scans
 __global__ void __launch_bounds__(256)
 k_csc_flat(const unsigned* __restrict__ heads, const int* __restrict__ win_first,
            const int* __restrict__ t_row, const double* __restrict__ t_val,
@@ -134,13 +144,13 @@ k_csc_flat(const unsigned* __restrict__ heads, const int* __restrict__ win_first
         const long long w = w0 + j, e = w * 32 + lane;
         const bool win = w < nwords, ok = win && e < nnz;
         row[j] = ok ? t_row[e] : -1;
-        val[j] = ok ? t_val[e] : 0.0;
+        val[j] = ok && !UNIT ? t_val[e] : 0.0;
         hd[j] = win ? heads[w] : 0u;
         first[j] = win ? win_first[w] : 0;
     }
     double prod[WPW];
 #pragma unroll
-    for (int j = 0; j < WPW; j++) prod[j] = row[j] >= 0 ? val[j] * t[row[j]] : 0.0;
+    for (int j = 0; j < WPW; j++) prod[j] = row[j] >= 0 ? (UNIT ? t[row[j]] : val[j] * t[row[j]]) : 0.0;
 #pragma unroll
     for (int j = 0; j < WPW; j++) {
         const unsigned below = hd[j] & (0xffffffffu >> (31 - lane));   // heads at or before this lane
@@ -227,14 +237,28 @@ LsNativeResult solve_ls_native(int rows, int cols, const int* rowptr, const int*
     DevBuf<double> partials(static_cast<size_t>(ceil_div(static_cast<long long>(len), 256)) + 1);
     DevBuf<CgState> state(1);
     const bool long_rows = rows > 0 && nnz / rows > 8;
+    // indicator matrix?  (MRB_LS_NO_UNIT=1 keeps the general kernels for A/B runs)
+    bool unit = false;
+    if (nnz > 0 && std::getenv("MRB_LS_NO_UNIT") == nullptr) {
+        DevBuf<int> not_one(1);
+        MRB_CUDA(cudaMemsetAsync(not_one.p, 0, sizeof(int), s));
+        k_all_ones<<<ceil_div(nnz, 256), 256, 0, s>>>(d_vals.p, nnz, not_one.p); MRB_LAUNCHED(1);
+        int h = 1;
+        MRB_CUDA(cudaMemcpyAsync(&h, not_one.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MRB_CUDA(cudaStreamSynchronize(s));
+        unit = h == 0;
+    }
     auto mul = [&](const double* v, double* out, const CgState* guard) {
         if (rows == 0) return;
-        if (long_rows)
-            k_csr_mul_warp<<<ceil_div(static_cast<long long>(rows) * 32, 256), 256, 0, s>>>(
-                d_rowptr.p, d_col.p, d_vals.p, v, out, rows, guard);
+        const int gw = ceil_div(static_cast<long long>(rows) * 32, 256), gt = ceil_div(rows, 256);
+        if (long_rows && unit)
+            k_csr_mul_warp<true><<<gw, 256, 0, s>>>(d_rowptr.p, d_col.p, d_vals.p, v, out, rows, guard);
+        else if (long_rows)
+            k_csr_mul_warp<false><<<gw, 256, 0, s>>>(d_rowptr.p, d_col.p, d_vals.p, v, out, rows, guard);
+        else if (unit)
+            k_csr_mul_thread<true><<<gt, 256, 0, s>>>(d_rowptr.p, d_col.p, d_vals.p, v, out, rows, guard);
         else
-            k_csr_mul_thread<<<ceil_div(rows, 256), 256, 0, s>>>(d_rowptr.p, d_col.p, d_vals.p, v,
-                                                                 out, rows, guard);
+            k_csr_mul_thread<false><<<gt, 256, 0, s>>>(d_rowptr.p, d_col.p, d_vals.p, v, out, rows, guard);
         MRB_LAUNCHED(1);
     };
     // row blocks for the segment split (any fixed table gives a deterministic summation order)
@@ -272,9 +296,13 @@ LsNativeResult solve_ls_native(int rows, int cols, const int* rowptr, const int*
     auto tmul = [&](const double* t, const double* v, double* out, double* dd, const CgState* guard) {
         if (cols == 0) return;
         if (use_flat) {
-            if (nwords > 0)
-                k_csc_flat<kFlatWpw><<<ceil_div(static_cast<long long>(ceil_div(nwords, kFlatWpw)) * 32, 256), 256, 0, s>>>(
-                    heads.p, win_first.p, t_row.p, t_val.p, t, piece_sum.p, nnz, nwords, guard);
+            const int gf = ceil_div(static_cast<long long>(ceil_div(nwords, kFlatWpw)) * 32, 256);
+            if (nwords > 0 && unit)
+                k_csc_flat<kFlatWpw, true><<<gf, 256, 0, s>>>(heads.p, win_first.p, t_row.p, t_val.p, t,
+                                                             piece_sum.p, nnz, nwords, guard);
+            else if (nwords > 0)
+                k_csc_flat<kFlatWpw, false><<<gf, 256, 0, s>>>(heads.p, win_first.p, t_row.p, t_val.p, t,
+                                                              piece_sum.p, nnz, nwords, guard);
             k_csc_fold_group<8><<<ceil_div(static_cast<long long>(cols) * 8, 256), 256, 0, s>>>(
                 col_piece_ptr.p, piece_sum.p, v, out, dd, cols, guard);
             MRB_LAUNCHED(2);

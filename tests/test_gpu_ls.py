@@ -116,6 +116,27 @@ def test_ls_native_bias_model(require_gpu, cpp_ls, oracle):
     assert info.iterations == it and info.solve_ms > 0
 
 
+def test_ls_native_indicator_matrix_skips_values_without_changing_bits(require_gpu, cpp_ls, monkeypatch):
+    """All stored values 1.0 (the bias model): the kernels that never read the value streams give
+    the bits of the general kernels; one value off 1.0 switches the general kernels back on."""
+    nu, ni, nnz = 2500, 900, 150000
+    u, i = synth.rating_pairs(nu, ni, nnz, 3, 3, seed=4)
+    raw = synth.planted_ratings(u, i, nu, ni, seed=4, subtract_median=False)
+    rowptr, col, vals, cols, b, x0 = synth.bias_model_system(u, i, raw, nu, ni, seed=4)
+    assert np.all(vals == 1.0)
+    x, it, rr = cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, algorithm=3, x0=x0)
+    monkeypatch.setenv("MRB_LS_NO_UNIT", "1")
+    xg, itg, rrg = cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, algorithm=3, x0=x0)
+    monkeypatch.delenv("MRB_LS_NO_UNIT")
+    assert it == itg and rr == rrg and np.array_equal(x, xg)
+    vals2 = vals.copy()
+    vals2[len(vals2) // 2] = 0.5
+    x2, it2, _ = cpp_ls.cg_least_squares(rowptr, col, vals2, cols, b, algorithm=3, x0=x0)
+    monkeypatch.setenv("MRB_LS_NO_UNIT", "1")
+    x2g, it2g, _ = cpp_ls.cg_least_squares(rowptr, col, vals2, cols, b, algorithm=3, x0=x0)
+    assert it2 == it2g and np.array_equal(x2, x2g) and not np.array_equal(x2, x)
+
+
 def test_ls_native_ragged_empty_and_termination(require_gpu, cpp_ls, oracle):
     rng = np.random.default_rng(8)
     rows, cols = 3000, 90
