@@ -84,6 +84,11 @@ MRB_API int als_from_python(int* user_ids, int* item_ids, int ratings_length, do
  * 2. Extensions: diagnostics.
  * ---------------------------------------------------------------------------------------- */
 MRB_API const char* mrb_last_error(void);   /* message of the last failing call on this thread */
+/* Thread safety: the five reference symbols and every call that takes no handle may be used from
+ * several threads at once (each call owns its streams and buffers; the thread count is atomic).
+ * A handle (mrb_als_problem, mrb_cosim, ...) is NOT re-entrant: it owns scratch buffers, work
+ * counters and streams that a second concurrent call on the same handle would share -- one
+ * thread per handle at a time. */
 MRB_API int mrb_device_count(void);         /* number of visible CUDA devices (0 if none / no driver) */
 MRB_API const char* mrb_build_info(void);   /* "sm_100a ..." */
 /* The library keeps freed device buffers in per-size free lists (repeated calls with the same
@@ -227,6 +232,9 @@ MRB_API int mrb_als_set_shard_partition(mrb_als_problem* p, int rank, int world,
 MRB_API int mrb_als_half_sweep(mrb_als_problem* p, int user_side, void* stream);
 /* Sum of this rank's per-movie residuals of the last movie half-sweep (synchronises stream). */
 MRB_API int mrb_als_shard_sse(mrb_als_problem* p, void* stream, double* out);
+/* Blocks until everything enqueued on `stream` (a cudaStream_t; 0 = the legacy default stream)
+ * has finished -- what a caller of mrb_als_half_sweep needs before mrb_als_get_factors. */
+MRB_API int mrb_als_stream_sync(mrb_als_problem* p, void* stream);
 /* CUDA-event time (ms) summed over the half-sweep launches since the last call. */
 MRB_API int mrb_als_collect_gram_ms(mrb_als_problem* p, float* out);
 /* Kernels launched by this library in this process so far. */

@@ -133,6 +133,8 @@ def _declare(dll):
     dll.mrb_als_set_shard_partition.argtypes = [c_void_p, c_int, c_int, c_int]
     dll.mrb_als_half_sweep.restype = c_int
     dll.mrb_als_half_sweep.argtypes = [c_void_p, c_int, c_void_p]
+    dll.mrb_als_stream_sync.restype = c_int
+    dll.mrb_als_stream_sync.argtypes = [c_void_p, c_void_p]
     dll.mrb_als_shard_sse.restype = c_int
     dll.mrb_als_shard_sse.argtypes = [c_void_p, c_void_p, _D]
     dll.mrb_als_collect_gram_ms.restype = c_int

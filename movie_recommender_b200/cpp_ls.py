@@ -234,7 +234,7 @@ class AlsProblem:
 
     def get_factors_synced(self):
         """get_factors after work enqueued on the legacy default stream (half_sweep(..., 0))."""
-        self.shard_sse(0)          # synchronises stream 0
+        _lib.check(_dll.mrb_als_stream_sync(self._h, ctypes.c_void_p(0)))
         return self.get_factors()
 
     def get_index(self):

@@ -1,6 +1,7 @@
 // C ABI (include/cpp_ls_b200.h).  Section 1 replaces cpp/ls_lib/ls_linux_dll.cpp:8-103.
 #include "../../include/cpp_ls_b200.h"
 
+#include <atomic>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -42,7 +43,7 @@ static int guarded(F&& body) {
 }
 
 // ls_linux_dll.cpp:6
-static int g_thread_count = 4;
+static std::atomic<int> g_thread_count{4};   // ctypes releases the GIL: callers may be threads
 
 static int solve_ls(int variant, int A_rows, int A_cols, const int* rowptr, const int* colidx,
                     const double* vals, int b_length, const double* b, int x_length, double* x,
@@ -75,7 +76,7 @@ static int solve_ls(int variant, int A_rows, int A_cols, const int* rowptr, cons
         op_holder.reset(new CsrFaithfulOp(A_rows, A_cols, nnz, d_rowptr.p, d_col.p, d_vals.p, s));
     }
     CsrFaithfulOp& op = *op_holder;
-    FaithfulCG cg(A_rows, A_cols, g_thread_count, s);
+    FaithfulCG cg(A_rows, A_cols, g_thread_count.load(std::memory_order_relaxed), s);
     CgResult r;
     {
         PhaseTimer t("  solve");
@@ -93,8 +94,8 @@ using namespace mrb;
 
 extern "C" {
 
-void set_thread_count(int thread_count) { g_thread_count = thread_count; }
-int get_thread_count(void) { return g_thread_count; }
+void set_thread_count(int thread_count) { g_thread_count.store(thread_count, std::memory_order_relaxed); }
+int get_thread_count(void) { return g_thread_count.load(std::memory_order_relaxed); }
 
 int cg_least_squares_from_python(int A_rows, int A_cols, int* A_row_indices, int* A_col_indices,
                                  double* A_values, int b_length, double* b_values, int x_length,
@@ -138,7 +139,7 @@ int als_from_python(int* user_ids, int* item_ids, int ratings_length, double* ra
         AlsRunInfo info;
         {
             PhaseTimer t("run");
-            info = p.run(algorithm, min_r_decrease, max_iteration, g_thread_count);
+            info = p.run(algorithm, min_r_decrease, max_iteration, g_thread_count.load(std::memory_order_relaxed));
         }
         PhaseTimer t("get_factors + teardown");
         if (!p.outputs_written()) p.get_factors(user_factors_values, item_factors_values);
@@ -566,6 +567,14 @@ int mrb_als_shard_sse(mrb_als_problem* p, void* stream, double* out) {
     return guarded([&] {
         MRB_REQUIRE(p != nullptr && out != nullptr, "null argument");
         *out = p->impl.shard_sse(static_cast<cudaStream_t>(stream));
+        return 0;
+    });
+}
+
+int mrb_als_stream_sync(mrb_als_problem* p, void* stream) {
+    return guarded([&] {
+        MRB_REQUIRE(p != nullptr, "null problem");
+        MRB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
         return 0;
     });
 }

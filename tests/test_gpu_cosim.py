@@ -111,3 +111,23 @@ def test_pair_score_is_computed_on_the_device(require_gpu):
     with pytest.raises(Exception):
         f._pair(0, len(shuffled))
     f.close()
+
+
+def test_catalogue_wider_than_one_shared_memory_part(require_gpu):
+    """The accumulators of a query live in shared memory, 13 824 movies per part: a catalogue of
+    15 000 movies is walked in two parts (movies on both sides of the cut, heavy and light
+    queries), ids and scores bit-equal to the oracle."""
+    genres, ratings = synthetic_catalogue(num_movies=15000, num_users=1200, density=0.01, seed=3)
+    f = finder_cls()(genres, ratings, buff_limit=0.2, buff_point=30)
+    o = SimilarOracle(genres, ratings, buff_limit=0.2, buff_point=30)
+    deg = np.array([len(d) for _, d in ratings])
+    queries = list(np.argsort(-deg)[:6]) + [0, 1, 6911, 6912, 7499, 7500, 13823, 13824, 14999]
+    seen = 0
+    for q in queries:
+        gi, gs = f.find_similar_movie(int(q))
+        oi, os_ = o.find_similar_movie(int(q))
+        assert list(gi) == list(oi), q
+        assert [float(s).hex() for s in gs] == [float(s).hex() for s in os_], q
+        seen += len(oi)
+    assert seen > 50
+    f.close()

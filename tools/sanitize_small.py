@@ -32,7 +32,31 @@ genres, ratings = synthetic_catalogue(num_movies=80, num_users=120, density=0.5,
 f = SimilarMovieFinder(genres, ratings)
 f.build()
 f.build(num_results=3)
+f._scaled_dot_product(0, 1)
+f.tune(ratings[0][0], ratings[1][0], 2, 10)
 f.close()
+# a catalogue wider than one shared-memory part (216 KB / 16 B = 13 824 movies): two parts
+genres, ratings = synthetic_catalogue(num_movies=15000, num_users=400, density=0.004, seed=2)
+f = SimilarMovieFinder(genres, ratings)
+f.build(length=300)
+f.close()
+# indicator matrix (the bias model): the kernels that skip the value streams
+u, i = synth.rating_pairs(300, 120, 9000, 3, 3, seed=7)
+raw = synth.planted_ratings(u, i, 300, 120, seed=7, subtract_median=False)
+rowptr, col, vals, cols, b, x0 = synth.bias_model_system(u, i, raw, 300, 120, seed=7)
+cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, algorithm=3, x0=x0)
+# two emulated ranks on one GPU, rows dealt: the owned-rows grouping
+p = synth.als_problem(90, 70, 4000, 7, seed=8, min_degrees=False)
+probs = [cpp_ls.AlsProblem(p["user_ids"], p["item_ids"], p["ratings"], 7, 90, 70) for _ in range(2)]
+for r, pr in enumerate(probs):
+    pr.set_factors(p["user_factors0"], p["item_factors0"])
+    pr.set_shard_partition(r, 2, 1)
+for side in (True, False):
+    for pr in probs:
+        pr.half_sweep(side, 0)
+        pr.shard_sse(0)
+for pr in probs:
+    pr.close()
 p = synth.als_problem(60, 50, 1500, 5, seed=6, min_degrees=False)
 fold_in_users(p["user_ids"], p["item_ids"], p["ratings"], 60, p["item_factors0"], 5)
 print("sanitize_small: done")
