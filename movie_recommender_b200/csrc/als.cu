@@ -1,4 +1,7 @@
 // ALS problem set-up and the reference-order sweep loop (see als.cuh).
+#include <exception>
+#include <thread>
+
 #include "als.cuh"
 
 #include "index_build.cuh"
@@ -68,14 +71,37 @@ AlsProblem::AlsProblem(const int* user_ids, const int* item_ids, int nnz, const 
     itf_.alloc(static_cast<size_t>(ni_) * k);
     // The ids go first on the compute stream; the ratings (half of the bytes, not needed by
     // the grouping) follow on the copy stream while the ids are being checked and grouped.
+    // Pageable ratings are staged by host threads and the call blocks: with the whole COO in hand
+    // that copy runs on a helper thread while this one checks and groups the ids.
+    std::thread helper;
+    std::exception_ptr helper_error;
     if (slice_len_ > 0) {
         copy_h2d(user_ids_.p + slice_begin_, user_ids, sizeof(int) * slice_len_, s_);
         copy_h2d(item_ids_.p + slice_begin_, item_ids, sizeof(int) * slice_len_, s_);
-        copy_h2d(ratings_.p + slice_begin_, ratings, sizeof(double) * slice_len_, s_copy_);
+        if (whole && copy_is_staged(ratings, sizeof(double) * slice_len_)) {
+            int device = 0;
+            MRB_CUDA(cudaGetDevice(&device));
+            helper = std::thread([&, device] {
+                try {
+                    MRB_CUDA(cudaSetDevice(device));
+                    copy_h2d(ratings_.p + slice_begin_, ratings, sizeof(double) * slice_len_, s_copy_);
+                } catch (...) {
+                    helper_error = std::current_exception();
+                }
+            });
+        } else {
+            copy_h2d(ratings_.p + slice_begin_, ratings, sizeof(double) * slice_len_, s_copy_);
+        }
     }
+    struct Joiner {
+        std::thread& t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } joiner{helper};
+    if (whole) build_index();
+    if (helper.joinable()) helper.join();
+    if (helper_error) std::rethrow_exception(helper_error);
     MRB_CUDA(cudaEventRecord(ev_ratings_, s_copy_));
     ratings_pending_ = true;
-    if (whole) build_index();
     cleanup.armed = false;
 }
 

@@ -62,6 +62,9 @@ void arena_trim();
 // source may be reused and is ordered after the work already enqueued on `s`; a staged download
 // returns when the data is in the destination.
 void copy_h2d(void* dev, const void* host, size_t bytes, cudaStream_t s);
+// true when copy_h2d / copy_d2h would stage this host buffer (pageable and large): the call then
+// BLOCKS the calling thread until the data has moved
+bool copy_is_staged(const void* host, size_t bytes);
 void copy_d2h(void* host, const void* dev, size_t bytes, cudaStream_t s);
 
 // RAII device allocation.

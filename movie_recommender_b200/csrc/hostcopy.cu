@@ -6,6 +6,8 @@
 // double buffers and enqueue them on their own streams, so the host-side memcpy of one chunk
 // overlaps the DMA of the others.  Page-locked sources / destinations and small copies take the
 // plain cudaMemcpyAsync path.
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -19,7 +21,17 @@ namespace {
 
 constexpr size_t STAGE_CHUNK = size_t(4) << 20;
 constexpr size_t STAGE_MIN = size_t(16) << 20;      // below this the plain path is as good
-constexpr int STAGE_THREADS = 4;
+constexpr int STAGE_THREADS_MAX = 16;
+// host threads that copy chunks into page-locked buffers; one memcpy thread moves ~10 GB/s, the
+// host link takes ~55 (MRB_STAGE_THREADS overrides)
+int stage_threads() {
+    static const int n = [] {
+        const char* e = std::getenv("MRB_STAGE_THREADS");
+        const int v = e ? std::atoi(e) : 8;
+        return std::max(1, std::min(STAGE_THREADS_MAX, v));
+    }();
+    return n;
+}
 
 struct Lane {
     cudaStream_t stream = nullptr;
@@ -30,11 +42,12 @@ struct Lane {
 struct Stager {
     std::mutex mu;               // one staged copy at a time per process
     int device = -1;
-    Lane lanes[STAGE_THREADS];
+    Lane lanes[STAGE_THREADS_MAX];
     void ensure(int dev) {
         if (device == dev) return;
         release();
-        for (Lane& l : lanes) {
+        for (int t = 0; t < stage_threads(); t++) {
+            Lane& l = lanes[t];
             MRB_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
             for (int b = 0; b < 2; b++) {
                 MRB_CUDA(cudaMallocHost(&l.buf[b], STAGE_CHUNK));
@@ -83,7 +96,8 @@ void staged_copy(char* dev, char* host, size_t bytes, bool h2d, cudaStream_t s) 
     MRB_CUDA(cudaEventCreateWithFlags(&before, cudaEventDisableTiming));
     MRB_CUDA(cudaEventRecord(before, s));
     const size_t chunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
-    cudaError_t errs[STAGE_THREADS];
+    const int STAGE_THREADS = stage_threads();
+    cudaError_t errs[STAGE_THREADS_MAX];
     std::vector<std::thread> pool;
     for (int t = 0; t < STAGE_THREADS; t++) {
         errs[t] = cudaSuccess;
@@ -132,6 +146,10 @@ void staged_copy(char* dev, char* host, size_t bytes, bool h2d, cudaStream_t s) 
 }
 
 }  // namespace
+
+bool copy_is_staged(const void* host, size_t bytes) {
+    return bytes >= STAGE_MIN && std::getenv("MRB_NO_STAGING") == nullptr && is_pageable(host);
+}
 
 void copy_h2d(void* dev, const void* host, size_t bytes, cudaStream_t s) {
     if (bytes == 0) return;
