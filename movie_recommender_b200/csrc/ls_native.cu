@@ -27,18 +27,49 @@ namespace {
 // UNIT: every stored value is exactly 1.0 (the indicator matrices of the bias model, config 2):
 // found once at upload (k_all_ones), the value streams are then not read at all -- 1.0 * x is x
 // bit for bit, so the results do not change.
+// One thread per FOUR short rows (r, r + T, r + 2T, r + 3T with T = threads of the grid, so every
+// load instruction stays coalesced): the rowptr -> column index -> gather chain of one row is
+// three dependent memory round trips; with a single row per thread the kernel ran at the latency
+// of that chain (ncu: 2.6 TB/s of DRAM, 83 % of the stall samples on the long scoreboard,
+// profiles/ncu_k_ls_native_C2_r02.txt).  The order of the additions inside a row is unchanged.
+constexpr int CSR_ROWS_PER_THREAD = 4;
 template <bool UNIT>
 __global__ void __launch_bounds__(256)
 k_csr_mul_thread(const int* __restrict__ rowptr, const int* __restrict__ colidx,
                  const double* __restrict__ vals, const double* __restrict__ x,
                  double* __restrict__ y, int rows, const CgState* __restrict__ guard) {
     if (guard && guard->done) return;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows) return;
-    double s = 0;
-    const int end = rowptr[r + 1];
-    for (int e = rowptr[r]; e < end; e++) s += UNIT ? x[colidx[e]] : vals[e] * x[colidx[e]];
-    y[r] = s;
+    const int T = gridDim.x * blockDim.x;
+    const int r0 = blockIdx.x * blockDim.x + threadIdx.x;
+    int beg[CSR_ROWS_PER_THREAD], end[CSR_ROWS_PER_THREAD], maxlen = 0;
+    double s[CSR_ROWS_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < CSR_ROWS_PER_THREAD; j++) {
+        const int r = r0 + j * T;
+        beg[j] = r < rows ? rowptr[r] : 0;
+        end[j] = r < rows ? rowptr[r + 1] : 0;
+        s[j] = 0;
+    }
+#pragma unroll
+    for (int j = 0; j < CSR_ROWS_PER_THREAD; j++) maxlen = max(maxlen, end[j] - beg[j]);
+    for (int o = 0; o < maxlen; o++) {
+        int c[CSR_ROWS_PER_THREAD];
+        double v[CSR_ROWS_PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < CSR_ROWS_PER_THREAD; j++) {
+            const bool in = beg[j] + o < end[j];
+            c[j] = in ? colidx[beg[j] + o] : -1;
+            v[j] = in && !UNIT ? vals[beg[j] + o] : 1.0;
+        }
+#pragma unroll
+        for (int j = 0; j < CSR_ROWS_PER_THREAD; j++)
+            if (c[j] >= 0) s[j] += UNIT ? x[c[j]] : v[j] * x[c[j]];
+    }
+#pragma unroll
+    for (int j = 0; j < CSR_ROWS_PER_THREAD; j++) {
+        const int r = r0 + j * T;
+        if (r < rows) y[r] = s[j];
+    }
 }
 
 __global__ void k_all_ones(const double* __restrict__ vals, int n, int* __restrict__ not_one) {
@@ -250,7 +281,8 @@ LsNativeResult solve_ls_native(int rows, int cols, const int* rowptr, const int*
     }
     auto mul = [&](const double* v, double* out, const CgState* guard) {
         if (rows == 0) return;
-        const int gw = ceil_div(static_cast<long long>(rows) * 32, 256), gt = ceil_div(rows, 256);
+        const int gw = ceil_div(static_cast<long long>(rows) * 32, 256);
+        const int gt = ceil_div(ceil_div(rows, CSR_ROWS_PER_THREAD), 256);
         if (long_rows && unit)
             k_csr_mul_warp<true><<<gw, 256, 0, s>>>(d_rowptr.p, d_col.p, d_vals.p, v, out, rows, guard);
         else if (long_rows)

@@ -105,8 +105,9 @@ def bench_c2(args, sampler):
                         "algorithmic_bytes_per_iteration": bytes_per_it, "peak_source": src,
                         "note": "every stored value of the bias model is 1.0: found at upload, the two value "
                                 "streams (2 x 8 x nnz = %d of the algorithmic bytes) are then not read -- "
-                                "bit-identical results (MRB_LS_NO_UNIT=1 keeps the general kernels: 0.555 instead "
-                                "of 0.512 ms per iteration at C2)" % (16 * nnz)}}
+                                "bit-identical results (MRB_LS_NO_UNIT=1 keeps the general kernels); history at C2: "
+                                "0.555 ms per iteration, 0.512 without the value streams, 0.439 with four rows "
+                                "per thread in A p (profiles/ncu_k_ls_native_C2_r02.txt)" % (16 * nnz)}}
     # parity: algorithm 1 is bit-identical to the reference (same iteration count, same bits)
     t0 = time.time()
     xf, itf, rrf = cpp_ls.cg_least_squares(rowptr, col, vals, cols, b, algorithm=1, x0=x0)
