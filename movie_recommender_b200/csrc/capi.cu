@@ -512,8 +512,9 @@ int mrb_als_download_factor_rows(mrb_als_problem* p, double* user_factors, doubl
         MRB_REQUIRE(p != nullptr, "null problem");
         p->impl.download_factor_rows(user_factors, item_factors, u_lo, u_hi, i_lo, i_hi,
                                      static_cast<cudaStream_t>(stream));
-        MRB_REQUIRE(!peer_barrier_timed_out(),
-                    "a peer barrier timed out: a rank of the group did not arrive");
+        if (peer_barrier_timed_out())
+            throw Error(kErrArgument, "a peer barrier timed out: a rank of the group did not arrive (" +
+                                          peer_barrier_timeout_report() + ")");
         return 0;
     });
 }

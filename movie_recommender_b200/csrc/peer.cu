@@ -2,8 +2,10 @@
 #include "peer.cuh"
 
 #include <atomic>
+#include <cstdio>
 #include <cstring>
 #include <map>
+#include <string>
 #include <mutex>
 
 namespace mrb {
@@ -42,7 +44,9 @@ __global__ void k_peer_barrier(PeerWords peers, int* mine, int rank, int world, 
             long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             if (t1 - t0 > 10000000000ll) {   // 10 s in ns
-                mine[PEER_MAX] = epoch;
+                mine[PEER_MAX] = epoch;                    // which barrier of this process
+                atomicOr(mine + PEER_MAX + 1, 1 << t);     // which peers were missing
+                mine[PEER_MAX + 2 + (t & 3)] = ld_acquire_sys(mine + t);   // a missing peer's last epoch
                 break;
             }
             __nanosleep(200);
@@ -79,6 +83,18 @@ bool peer_barrier_timed_out() {
     int v = 0;
     MRB_CUDA(cudaMemcpy(&v, g_words + PEER_MAX, sizeof(int), cudaMemcpyDeviceToHost));
     return v != 0;
+}
+
+std::string peer_barrier_timeout_report() {
+    if (g_words == nullptr) return "no barrier words";
+    int v[PEER_MAX + 8];
+    MRB_CUDA(cudaMemcpy(v, g_words, sizeof(v), cudaMemcpyDeviceToHost));
+    char buf[256];
+    std::snprintf(buf, sizeof(buf),
+                  "barrier %d of this process timed out (enqueued so far: %d), missing ranks mask 0x%x, "
+                  "arrival words %d %d %d %d %d %d %d %d",
+                  v[PEER_MAX], g_epoch.load(), v[PEER_MAX + 1], v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    return buf;
 }
 
 void ipc_export(void* d_ptr, unsigned char* handle64) {

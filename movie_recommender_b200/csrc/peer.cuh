@@ -2,6 +2,7 @@
 // CUDA IPC mappings of the peers' buffers and a device-side barrier over them, so that the two
 // half-sweeps of a sweep chain on the stream without a host round trip or a library collective.
 #pragma once
+#include <string>
 #include "common.cuh"
 
 namespace mrb {
@@ -20,7 +21,8 @@ int* peer_barrier_words();
 // ~10 s timeout that is reported by peer_barrier_timed_out() instead of hanging the GPU.
 void enqueue_peer_barrier(int* const* peer_words /* [world], own entry ignored */, int rank,
                           int world, cudaStream_t s);
-bool peer_barrier_timed_out();   // after a stream synchronisation
+bool peer_barrier_timed_out();
+std::string peer_barrier_timeout_report();   // which barrier, which ranks were missing   // after a stream synchronisation
 
 // Peer mappings are cached by handle for the life of the process: the arena hands a re-created
 // problem the same device blocks, so a training loop that builds one problem per step opens

@@ -218,7 +218,9 @@ class ShardedAls:
         dist.all_reduce(need, op=dist.ReduceOp.MAX)
         if float(need.item()) > 0:
             c0 = time.time()
-            for _ in range(max(8, int(0.6 / max(wall_ms / steps * 1e-3, 1e-4)))):
+            # the count must be the SAME on every rank (every sweep holds two device barriers):
+            # it is derived from the all-reduced device time, never from this rank's own clock
+            for _ in range(max(8, int(0.6 / max(float(ms[0]) / steps * 1e-3, 1e-4)))):
                 self.sweep()
             torch.cuda.synchronize()
             if sampler is not None:
