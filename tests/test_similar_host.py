@@ -98,6 +98,8 @@ def test_marshalling_and_scaled_dot_product(Finder):
     x = 3 + (3 * math.exp(0.1) - 3) * (4 - 3) / (10 - 3)
     assert table[3] == 0.0 and table[4] == math.log(x) - math.log(3)
     with pytest.raises(ValueError):
+        Finder({1: [0, 0, 2]}, [(1, {10: 3.0})])                 # genres with duplicates are no set
+    with pytest.raises(ValueError):
         Finder({1: {0}}, [(1, {10: 3.3})])                       # off the 0.5 grid
     with pytest.raises(ValueError):
         Finder.from_arrays({}, [1, 2], [1, 0], [5, 6], [1.0, 2.0])   # not grouped by movie
