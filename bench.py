@@ -202,6 +202,19 @@ def algorithmic_bytes_per_sweep(w):
     return b_u + b_i
 
 
+def compulsory_bytes_per_sweep(w):
+    """SURVEY.md section 8d's second model ("each array once"): what a sweep must move if every
+    gathered factor row came from cache after its first touch -- grouped ids + ratings streamed
+    once per side, the opposite factor matrix read once, the own factor rows read (warm start)
+    and written once, the row pointers.  The ncu DRAM traffic is compared with THIS figure (the
+    no-cache figure above is the roofline numerator)."""
+    nnz, k, nu, ni = w["num_ratings"], w["k"], w["num_users"], w["num_items"]
+    uf, itf = nu * (k + 1) * 8, ni * k * 8
+    c_u = nnz * (4 + 8) + itf + 2 * uf + (nu + 1) * 4
+    c_i = nnz * (4 + 8) + uf + 2 * itf + (ni + 1) * 4
+    return c_u + c_i
+
+
 def algorithmic_flops_per_sweep(w):
     """F_u + F_i (symmetric SYRK + right-hand side per rating) plus the
     Cholesky factorisations nu (k+1)^3 / 3 + ni k^3 / 3.  This is what the roofline fraction is
@@ -626,6 +639,7 @@ def main():
                     "no N > 1 ncu capture (ncu is a one-GPU tool here); see the N = 1 line",
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes / 2.0 / world,
+                    "compulsory_bytes_per_launch": compulsory_bytes_per_sweep(w) / 2.0 / world,
                     "avg_launch_ms": per_launch_ms,
                     "note": "gather bytes counted once per rating (SURVEY 8d); the kernel is "
                             "fp64-tensor bound, see roofline_fp64"}

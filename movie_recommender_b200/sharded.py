@@ -1,19 +1,22 @@
 """Multi-GPU ALS: one process per GPU, ``torch.distributed`` for the
-plumbing (rendezvous, the stream-ordered barrier, max-over-ranks timing), hand-written CUDA for
+plumbing (rendezvous, the 384-byte handle exchange, max-over-ranks timing), hand-written CUDA for
 everything on the data path.
 
-Partitioning: the degree-sorted users, then movies, are dealt over the ``world`` ranks (or cut
-into contiguous cost-balanced ranges for the NCCL baseline); every rank keeps the whole COO,
-both groupings and full replicas of both factor matrices (C3: 2 GB per GPU), only the WORK is
-sharded.  Exchange: the one place the path shards is
-the all-gather of the freshly solved factor rows after each half-sweep.  Two implementations:
+Partitioning: the degree-sorted users, then movies, are dealt over the ``world`` ranks in snake
+order (or cut into contiguous cost-balanced ranges for the NCCL baseline); every rank holds the
+COO and full replicas of both factor matrices, but uploads only its 1/world slice (the slices are
+pushed to the peers over NVLink) and groups only the rows it owns.  Exchange: the one place the
+path shards is the all-gather of the freshly solved factor rows after each half-sweep.  Two
+implementations:
 
 * ``exchange="p2p"`` (default, the product): the solve kernel stores every solved row into all
   replicas through NVLink peer pointers (CUDA IPC mappings of the other ranks' buffers), i.e. the
   all-gather is fused into the producing kernel and overlaps the math row by row; between
-  half-sweeps only a one-element NCCL all-reduce remains, as a stream-ordered barrier.
-* ``exchange="nccl"`` (the baseline it is compared with): rows are written locally and the ranges
-  are exchanged with ``torch.distributed.all_gather`` on tensors aliasing the library's buffers.
+  half-sweeps only a device-side flag barrier over the same mappings remains (``csrc/peer.cu``),
+  enqueued on the stream -- no host round trip, no library collective.
+* ``exchange="nccl"`` (the baseline it is compared with): every rank uploads everything, rows are
+  written locally and the contiguous ranges are exchanged with ``torch.distributed.all_gather``
+  on tensors aliasing the library's buffers.
 """
 import numpy as np
 

@@ -52,3 +52,16 @@ def test_reference_sample_keeps_the_shrink_rule():
     assert s["user_ids"].max() == s["num_users"] - 1 and s["item_ids"].max() == s["num_items"] - 1
     assert len(s["user_factors0"]) == s["num_users"] * (w["k"] + 1)
     assert "shrink rule" in b.sample_description(s, w)
+
+
+def test_compulsory_bytes_match_the_survey():
+    """SURVEY.md 8d, "each array once": per side 333 MB of grouped ids + ratings, the opposite
+    factor matrix once (21.6 / 115.6 MB), the own rows read and written."""
+    b = load_bench()
+    w = b.WORKLOAD
+    nnz, uf, itf = w["num_ratings"], 283228 * 51 * 8, 53889 * 50 * 8
+    want = 2 * nnz * 12 + (itf + 2 * uf) + (uf + 2 * itf) + (283229 + 53890) * 4
+    assert b.compulsory_bytes_per_sweep(w) == want
+    assert abs(want / 1e9 - 1.08) < 0.01
+    # far below the no-cache figure the roofline numerator uses
+    assert b.compulsory_bytes_per_sweep(w) < b.algorithmic_bytes_per_sweep(w) / 20
