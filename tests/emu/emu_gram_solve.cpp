@@ -7,11 +7,16 @@
 #include <vector>
 
 namespace {
+// peers / row_offset: the fused all-gather of the multi-GPU path -- the solved row is also stored
+// at peers[j] + row_offset of every other replica (GramArgs::x_peers, NVLink peer memory on the GPU)
 template <int M8, int VARIANT>
-void run(int n, const double* aug, int ld, double* x, double* sse) {
+void run(int n, const double* aug, int ld, double* x, double* sse, int n_peers = 0,
+         double* const* peers = nullptr, size_t row_offset = 0) {
     constexpr int ST = M8 * (M8 + 1) / 2;
     warp_emu::Warp warp;
     mrb::GramArgs args{};
+    args.n_peers = n_peers;
+    for (int j = 0; j < n_peers; j++) args.x_peers[j] = peers[j];
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; lane++)
         lanes.emplace_back([&, lane] {
@@ -25,7 +30,7 @@ void run(int n, const double* aug, int ld, double* x, double* sse) {
                 for (int tj = 0; tj <= ti; tj++)
                     for (int h = 0; h < 2; h++)
                         acc[mrb::TI(ti, tj)][h] = aug[(8 * ti + p) * ld + 8 * tj + 2 * q + h];
-            mrb::gram_solve<M8, VARIANT>(acc, n, x, sse, lane, args, 0);
+            mrb::gram_solve<M8, VARIANT>(acc, n, x, sse, lane, args, row_offset);
         });
     for (auto& t : lanes) t.join();
 }
@@ -36,16 +41,18 @@ void run(int n, const double* aug, int ld, double* x, double* sse) {
 // sse: receives s - (residual bookkeeping) = sum of squared residuals at the solution.
 namespace {
 template <int VARIANT>
-int dispatch(int m8, int n, const double* aug, int ld, double* x, double* sse) {
+int dispatch(int m8, int n, const double* aug, int ld, double* x, double* sse, int n_peers = 0,
+             double* const* peers = nullptr, size_t row_offset = 0) {
     if (n + 1 > 8 * m8 || n + 1 <= 8 * (m8 - 1)) return -2;   // the rhs must sit in the last tile row
+    if (n_peers < 0 || n_peers > 8) return -4;
     switch (m8) {
-        case 1: run<1, VARIANT>(n, aug, ld, x, sse); break;
-        case 2: run<2, VARIANT>(n, aug, ld, x, sse); break;
-        case 3: run<3, VARIANT>(n, aug, ld, x, sse); break;
-        case 4: run<4, VARIANT>(n, aug, ld, x, sse); break;
-        case 5: run<5, VARIANT>(n, aug, ld, x, sse); break;
-        case 6: run<6, VARIANT>(n, aug, ld, x, sse); break;
-        case 7: run<7, VARIANT>(n, aug, ld, x, sse); break;
+        case 1: run<1, VARIANT>(n, aug, ld, x, sse, n_peers, peers, row_offset); break;
+        case 2: run<2, VARIANT>(n, aug, ld, x, sse, n_peers, peers, row_offset); break;
+        case 3: run<3, VARIANT>(n, aug, ld, x, sse, n_peers, peers, row_offset); break;
+        case 4: run<4, VARIANT>(n, aug, ld, x, sse, n_peers, peers, row_offset); break;
+        case 5: run<5, VARIANT>(n, aug, ld, x, sse, n_peers, peers, row_offset); break;
+        case 6: run<6, VARIANT>(n, aug, ld, x, sse, n_peers, peers, row_offset); break;
+        case 7: run<7, VARIANT>(n, aug, ld, x, sse, n_peers, peers, row_offset); break;
         default: return -2;
     }
     return 0;
@@ -59,5 +66,17 @@ extern "C" int emu_gram_solve(int variant, int m8, int n, const double* aug, int
     if (variant == 0) return dispatch<0>(m8, n, aug, ld, x, sse);
     if (variant == 2) return dispatch<2>(m8, n, aug, ld, x, sse);
     if (variant == 3) return dispatch<3>(m8, n, aug, ld, x, sse);
+    return -3;
+}
+
+// The same with the fused peer stores of the N-GPU path: x is this rank's row (xo = replica +
+// row_offset on the device), peers[j] the BASE of replica j; the solved row must land at
+// peers[j] + row_offset .. + n in every replica and nowhere else.
+extern "C" int emu_gram_solve_peers(int variant, int m8, int n, const double* aug, int ld, double* x,
+                                    double* sse, int n_peers, double* const* peers,
+                                    unsigned long long row_offset) {
+    if (variant == 0) return dispatch<0>(m8, n, aug, ld, x, sse, n_peers, peers, row_offset);
+    if (variant == 2) return dispatch<2>(m8, n, aug, ld, x, sse, n_peers, peers, row_offset);
+    if (variant == 3) return dispatch<3>(m8, n, aug, ld, x, sse, n_peers, peers, row_offset);
     return -3;
 }

@@ -92,3 +92,47 @@ def test_fewer_ratings_than_unknowns(emu):
     x0 = rng.uniform(-1, 1, 11)
     x, sse = emu(A, b, x0)
     assert np.all(np.isfinite(x)) and np.max(np.abs(A @ x - b)) <= 1e-6 and abs(sse) <= 1e-6
+
+
+@pytest.mark.parametrize("n,n_peers", [(51, 7), (50, 1), (11, 3), (33, 2)])
+def test_fused_peer_stores_write_the_row_into_every_replica(n, n_peers):
+    """The N-GPU exchange is fused into the solve (GramArgs::x_peers): the lane-linear store of the
+    solved row goes to this rank's replica AND to ``peers[j] + row_offset`` of every other one.
+    On the emulated warp: every replica receives exactly the solved row at the owner's offset,
+    the canaries around it stay untouched, and the solution equals the single-GPU one."""
+    subprocess.run(["make", "-C", EMU_DIR], check=True, capture_output=True)
+    lib = ctypes.CDLL(os.path.join(EMU_DIR, "libemu_gram.so"))
+    D = ctypes.POINTER(ctypes.c_double)
+    lib.emu_gram_solve.restype = ctypes.c_int
+    lib.emu_gram_solve.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, D, ctypes.c_int, D, D]
+    lib.emu_gram_solve_peers.restype = ctypes.c_int
+    lib.emu_gram_solve_peers.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, D, ctypes.c_int, D, D,
+                                         ctypes.c_int, ctypes.POINTER(D), ctypes.c_ulonglong]
+    rng = np.random.default_rng(100 * n + n_peers)
+    ratings = 3 * n
+    A, b = rng.uniform(-1, 1, (ratings, n)), rng.normal(0, 1, ratings)
+    x0 = rng.uniform(-1, 1, n)
+    m8 = (n + 1 + 7) // 8
+    ld = 8 * m8
+    Ab = np.hstack([A, b[:, None]])
+    aug = np.zeros((ld, ld))
+    aug[:n + 1, :n + 1] = Ab.T @ Ab
+    owners, owner = 5, 3                                  # the solved row is row 3 of 5
+    row_offset = owner * n
+    CANARY = -777.25
+    replicas = [np.full(owners * n, CANARY) for _ in range(n_peers)]
+    peer_ptrs = (D * n_peers)(*[r.ctypes.data_as(D) for r in replicas])
+    x = x0.copy()
+    sse = ctypes.c_double(np.nan)
+    rc = lib.emu_gram_solve_peers(3, m8, n, aug.ctypes.data_as(D), ld, x.ctypes.data_as(D),
+                                  ctypes.byref(sse), n_peers, peer_ptrs, row_offset)
+    assert rc == 0
+    x1 = x0.copy()
+    sse1 = ctypes.c_double(np.nan)
+    assert lib.emu_gram_solve(3, m8, n, aug.ctypes.data_as(D), ld, x1.ctypes.data_as(D),
+                              ctypes.byref(sse1)) == 0
+    assert np.array_equal(x.view(np.uint64), x1.view(np.uint64)) and sse.value == sse1.value
+    for r in replicas:
+        got = r.reshape(owners, n)
+        assert np.array_equal(got[owner].view(np.uint64), x.view(np.uint64))
+        assert np.all(np.delete(got, owner, axis=0) == CANARY)
