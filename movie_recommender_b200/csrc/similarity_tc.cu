@@ -47,7 +47,7 @@ constexpr int TC_PEND = 32;        // pending buffer per query
 // one-pass mode keeps per-row lists in shared memory and needs one owner thread per row; the
 // two-pass modes keep nothing per row, so 4 groups split every tile's 8 chunks of 16 columns:
 // 4 warps per scheduler hide the TMEM / vote latencies a single warp per scheduler exposes
-// (one group: 2.9 ms for the collect pass at config 4, profiles/launches_sim_r02.csv).
+// (one group: 2.9 ms for the collect pass at config 4, profiles/launches_sim_C4_r02.csv).
 template <int MODE> constexpr int tc_sets() { return MODE == 0 ? 1 : 4; }
 template <int MODE> constexpr int tc_threads() { return 64 + 128 * tc_sets<MODE>(); }
 constexpr int TC_TILE_BYTES = TC_N * TC_KB * 4;          // one K block of one tile: 16 KB
