@@ -4,32 +4,11 @@ symbols as the reference's cpp_ls.py, so pointing it at the UNMODIFIED reference
 checks the marshalling (dtypes, lengths, in/out buffers, c_double wrapping, the algorithm-2 symbol
 name) and the order in which the initial vectors are drawn from the global NumPy RNG
 (python/full_data/cpp_ls.py:92, :150-151) without a GPU."""
-import ctypes
-
 import numpy as np
 import pytest
 
 from conftest import bits_equal, load_golden
 from oracle import oracle
-
-
-@pytest.fixture()
-def cpp_ls_on_reference(monkeypatch):
-    if not oracle.has_ref():
-        pytest.skip("oracle/_ref/cpp_ls_lib.so not built (reference sources absent)")
-    from movie_recommender_b200 import _lib, cpp_ls
-    ref = ctypes.CDLL(oracle.ref_path())
-    c_int, c_double, I, D = ctypes.c_int, ctypes.c_double, _lib._I, _lib._D
-    ref.set_thread_count.restype = None
-    ref.set_thread_count.argtypes = [c_int]
-    ref.get_thread_count.restype = c_int
-    for name in ("cg_least_squares_from_python", "cg_least_squares2_from_python"):
-        getattr(ref, name).restype = c_int
-        getattr(ref, name).argtypes = [c_int, c_int, I, I, D, c_int, D, c_int, D, c_double, c_int, D]
-    ref.als_from_python.restype = c_int
-    ref.als_from_python.argtypes = [I, I, c_int, D, c_int, c_int, D, c_int, D, c_double, c_int, c_int]
-    monkeypatch.setattr(cpp_ls, "_dll", ref)
-    return cpp_ls
 
 
 @pytest.mark.parametrize("T", [1, 4])
