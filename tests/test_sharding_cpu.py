@@ -138,3 +138,23 @@ def test_similarity_query_blocks_world2_gloo(tmp_path):
                           "29519", str(script)], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_dealt_partition_properties_for_every_world_size():
+    """The driver's scaling run uses N = 1, 2, 4, 8: for each (and an odd one) the dealt shares
+    are disjoint, cover every row, are processed longest first, and balance ratings + solve cost
+    to within one heavy row -- on a power-law degree profile like the ML-27M users."""
+    rng = np.random.default_rng(8)
+    rows = 5003                                               # not a multiple of any world size
+    deg = np.minimum((rng.pareto(1.2, rows) * 40 + 11).astype(np.int64), 9000)
+    ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    for world in (1, 2, 3, 4, 8):
+        shares = [cpp_ls.dealt_owners(ptr, r, world) for r in range(world)]
+        flat = np.concatenate(shares)
+        assert len(flat) == rows and len(np.unique(flat)) == rows
+        sizes = [len(s) for s in shares]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+        cost = [float(deg[s].sum() + 100 * len(s)) for s in shares]
+        for s in shares:
+            assert np.all(np.diff(deg[s]) <= 0)
+        assert max(cost) - min(cost) <= deg.max() + 100, (world, cost)
